@@ -1,0 +1,1118 @@
+// fq3_decode.cuh -- the persistent decode kernel (sm_100a).
+//
+// One cooperative launch runs a whole chunk of codec frames on device: per frame the 15-pass code predictor
+// (reference: faster_qwen3_tts/predictor_graph.py:115-167), the 16-row embedding sum (generate.py:163-171), the
+// 28-layer talker step (talker_graph.py:97-107,198-214), codec_head, repetition penalty and sampling
+// (generate.py:182-197, sampling.py:10-66) and the EOS / max-length control flow (generate.py:149-151,175-177).
+// No per-token launch, graph replay or host round trip remains inside a chunk.
+//
+// Structure of a CTA (one per SM, 288 threads):
+//   warp 8      PRODUCER: walks this CTA's slice of the weight "tape" (weights pre-packed at load time into
+//               the exact order they are consumed) and streams it with cp.async.bulk (TMA bulk copy, SASS
+//               UBLKCP) into a 5 x 32 KB shared-memory ring guarded by full/empty mbarriers.  It never takes
+//               part in grid barriers, so HBM keeps streaming while the consumers synchronise / do attention.
+//   warps 0..7  CONSUMERS: fp32-accumulate GEMV rows straight out of the ring (conflict-free 16-byte LDS),
+//               warp-shuffle reductions, fused epilogues (residual add, SiLU*up, bias), RMSNorm prologues,
+//               GQA attention over the KV cache, and block-wide sampling.  Everything that is cheap is
+//               computed redundantly in every CTA (norms, sampling, embedding sums) so that only five grid
+//               barriers per layer remain.
+//
+// Numerics follow the reference's eager bf16 / fp32 rounding points (template parameter BF): products of
+// dtype-rounded operands are accumulated in fp32 and rounded to the model dtype wherever torch would
+// materialise a tensor.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace fq3 {
+
+constexpr int NCW = 8;               // consumer warps
+constexpr int NCT = NCW * 32;        // consumer threads
+constexpr int NTHREADS = NCT + 32;   // + producer warp
+constexpr int NS = 5;                // ring stages
+constexpr int STAGE_BYTES = 32768;
+constexpr int XS_FLOATS = 6144;      // activation vector(s) feeding the current GEMV; also attention/sampling scratch
+constexpr int HMAX = 2048;           // max talker hidden (xin / past_hidden buffers)
+constexpr int VMAX = 4096;
+constexpr int MAXGRP = 512;          // row groups per CTA
+constexpr int MAXSEG = 256;          // GEMV segments
+constexpr int SEQMAX = 4096;
+
+enum Mode { MODE_FUSED = 0, MODE_TALKER_STEP = 1, MODE_PRED_RUN = 2 };
+
+struct Grp {           // one row group of one segment, as seen by one CTA (<= 32 rows, full K)
+  uint32_t off16;      // tape offset / 16
+  int32_t row0;        // first row (index inside the segment)
+  uint16_t rows;       // even
+  uint16_t m;          // 512-byte row chunks per tile
+  uint16_t ntiles;     // K-chunks
+  uint16_t pad;
+};
+
+struct Sampling {
+  int do_sample, top_k;
+  float temperature, top_p, penalty;
+};
+
+struct StackDev {
+  int H, I, L, nH, nKV, V, qd, kd, rep;
+  float eps;
+  int seg_base;        // segment id of layer 0 / QKV; layer l uses seg_base + 4*l + {0:QKV,1:O,2:GU,3:DN}
+  int seg_head;        // first head segment
+  const void *ln_in, *ln_post, *qnorm, *knorm, *ln_f;
+  void *kc, *vc;       // [L][nKV][S][128] model dtype
+  int S;
+  const float *cos, *sin;  // [npos][128] fp32
+  int npos;
+};
+
+struct KParams {
+  StackDev t, p;
+  int mode, ncta, nseg, seg_mtp;
+  const uint8_t* tape;
+  const Grp* grps;
+  const uint32_t* segtab;       // [cta][nseg] : (begin << 8) | n   (begin relative to this CTA's first group)
+  const uint32_t* cta_grp_off;  // [ncta + 1]
+  float *X, *X1, *QKV, *ATT, *ACT, *LOGITS;
+  int ldX, ldQKV, ldATT, ldACT;
+  unsigned* bar;
+  const void* t_embed;
+  const void* p_embeds;
+  const void* mtp_b;
+  int has_mtp, ncb, eos;
+  int* state;          // [0] token [1] step [2] gen_step [3] finished [4] emitted(last launch)
+  float* past_hidden;  // [Ht] fp32 holding dtype-rounded values
+  uint32_t* seen;      // [VMAX/32] bitmap of cb0 history (sampling.py:22 unique())
+  int prefill_len, rope_delta, n_left_pad, max_new, min_new, trailing_len, max_seq_len;
+  const void* trailing;
+  const void* tts_pad;
+  const float* uniforms;
+  Sampling sp_t, sp_p;
+  int n_frames;
+  long long* codes_out;
+  const void* in_embeds;
+  void* hidden_out;
+  int position;
+  const void* pred_input;
+  const float* pred_uniforms;
+  float* dbg;
+  int dbg_on;
+  long long dbg_stride_layer;  // floats per layer record
+};
+
+// ------------------------------------------------------------------------------------------------------------
+// PTX helpers
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* b, uint32_t cnt) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(cnt) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* b, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* b) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* b, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(b)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
+  while (!mbar_try_wait(b, parity)) {
+  }
+}
+// TMA bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void csync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }  // consumers only
+
+template <bool BF>
+__device__ __forceinline__ float rnd(float x) {
+  if constexpr (BF)
+    return __bfloat162float(__float2bfloat16_rn(x));
+  else
+    return x;
+}
+template <bool BF>
+__device__ __forceinline__ float ldw(const void* p, size_t i) {  // read-only weight / table element
+  if constexpr (BF)
+    return __bfloat162float(__ldg(reinterpret_cast<const __nv_bfloat16*>(p) + i));
+  else
+    return __ldg(reinterpret_cast<const float*>(p) + i);
+}
+template <bool BF>
+__device__ __forceinline__ void stw(void* p, size_t i, float v) {
+  if constexpr (BF)
+    reinterpret_cast<__nv_bfloat16*>(p)[i] = __float2bfloat16_rn(v);
+  else
+    reinterpret_cast<float*>(p)[i] = v;
+}
+__device__ __forceinline__ float bf_lo(uint32_t u) { return __uint_as_float(u << 16); }
+__device__ __forceinline__ float bf_hi(uint32_t u) { return __uint_as_float(u & 0xffff0000u); }
+
+// ------------------------------------------------------------------------------------------------------------
+// shared memory layout
+// ------------------------------------------------------------------------------------------------------------
+struct __align__(128) Smem {
+  uint8_t ring[NS][STAGE_BYTES];
+  float xs[XS_FLOATS];
+  float xin[2][HMAX];
+  float hid[HMAX];
+  Grp grp[MAXGRP];
+  uint32_t seg[MAXSEG];
+  uint64_t full[NS];
+  uint64_t empty[NS];
+  float red[NCW];
+  int hist[256];
+  uint32_t seen[VMAX / 32];
+  int codes[16];
+  int ibc[4];               // integer broadcast slots
+  float fbc[4];             // float broadcast slots
+  volatile int stop_flag;   // consumers -> producer
+  volatile int prod_done;   // producer -> consumers
+  volatile int prod_issued; // tiles issued by the producer
+};
+
+struct Ctx {
+  const KParams& P;
+  Smem& s;
+  int tid, warp, lane;
+  uint32_t tile_ctr;   // tiles consumed (identical in every consumer thread)
+  unsigned bar_target; // thread 0 only
+};
+
+// ------------------------------------------------------------------------------------------------------------
+// grid barrier (consumer warps of all CTAs).  The producer warp never waits here.
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void grid_sync(Ctx& c) {
+  csync();
+  if (c.tid == 0) {
+    c.bar_target += (unsigned)c.P.ncta;
+    __threadfence();
+    atomicAdd(c.P.bar, 1u);
+    while (ld_acquire_u32(c.P.bar) < c.bar_target) {
+    }
+    __threadfence();
+  }
+  csync();
+}
+
+__device__ __forceinline__ float block_sum(Ctx& c, float v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if (c.lane == 0) c.s.red[c.warp] = v;
+  csync();
+  float r = 0.f;
+#pragma unroll
+  for (int w = 0; w < NCW; ++w) r += c.s.red[w];
+  csync();
+  return r;
+}
+__device__ __forceinline__ float block_max(Ctx& c, float v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  if (c.lane == 0) c.s.red[c.warp] = v;
+  csync();
+  float r = c.s.red[0];
+#pragma unroll
+  for (int w = 1; w < NCW; ++w) r = fmaxf(r, c.s.red[w]);
+  csync();
+  return r;
+}
+
+// RMSNorm (transformers Qwen3 RMSNorm: fp32 variance, x*rsqrt(var+eps) -> dtype, weight * that) of a global fp32
+// vector into shared memory.  Every CTA computes it redundantly.
+template <bool BF>
+__device__ __forceinline__ void norm_to_smem(Ctx& c, const float* src, const void* w, size_t woff, int H, float eps,
+                                             float* dst) {
+  float ss = 0.f;
+  for (int k = c.tid; k < H; k += NCT) {
+    float v = __ldcg(src + k);
+    dst[k] = v;
+    ss += v * v;
+  }
+  ss = block_sum(c, ss);
+  const float r = 1.0f / sqrtf(ss / (float)H + eps);
+  for (int k = c.tid; k < H; k += NCT) dst[k] = rnd<BF>(ldw<BF>(w, woff + k) * rnd<BF>(dst[k] * r));
+  csync();
+}
+// same, source already in shared memory (layer 0 input held locally)
+template <bool BF>
+__device__ __forceinline__ void norm_smem_to_smem(Ctx& c, const float* src, const void* w, size_t woff, int H,
+                                                  float eps, float* dst) {
+  float ss = 0.f;
+  for (int k = c.tid; k < H; k += NCT) {
+    float v = src[k];
+    ss += v * v;
+  }
+  ss = block_sum(c, ss);
+  const float r = 1.0f / sqrtf(ss / (float)H + eps);
+  for (int k = c.tid; k < H; k += NCT) dst[k] = rnd<BF>(ldw<BF>(w, woff + k) * rnd<BF>(src[k] * r));
+  csync();
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// GEMV over one segment: rows of this CTA, streamed from the ring.  x: shared memory, NT vectors of stride xstride.
+// Epilogue epi(row0, v0[NT], v1[NT]) is called by lane 0 for each row pair (rows row0, row0+1).
+// ------------------------------------------------------------------------------------------------------------
+template <bool BF, int NT, class Epi>
+__device__ __forceinline__ void gemv_seg(Ctx& c, int seg, const float* x, int xstride, Epi epi) {
+  constexpr int EPL = BF ? 8 : 4;  // elements per lane per 16-byte load
+  const uint32_t st = c.s.seg[seg];
+  const int gbeg = (int)(st >> 8), gn = (int)(st & 255u);
+  for (int gi = 0; gi < gn; ++gi) {
+    const Grp g = c.s.grp[gbeg + gi];
+    const int npairs = g.rows >> 1;
+    const int m = g.m;
+    float acc[4][NT];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int t = 0; t < NT; ++t) acc[a][t] = 0.f;
+    for (int tl = 0; tl < g.ntiles; ++tl) {
+      const int stage = (int)(c.tile_ctr % NS);
+      const uint32_t par = (c.tile_ctr / NS) & 1u;
+      mbar_wait(&c.s.full[stage], par);
+      const uint8_t* tile = c.s.ring[stage];
+      for (int j = 0; j < m; ++j) {
+        const int kb = tl * m + j;
+        float xv[NT][EPL];
+#pragma unroll
+        for (int t = 0; t < NT; ++t) {
+          if constexpr (BF) {
+            const float4 a = *reinterpret_cast<const float4*>(x + t * xstride + kb * 256 + c.lane * 4);
+            const float4 b = *reinterpret_cast<const float4*>(x + t * xstride + kb * 256 + 128 + c.lane * 4);
+            xv[t][0] = a.x; xv[t][1] = a.y; xv[t][2] = a.z; xv[t][3] = a.w;
+            xv[t][4] = b.x; xv[t][5] = b.y; xv[t][6] = b.z; xv[t][7] = b.w;
+          } else {
+            const float4 a = *reinterpret_cast<const float4*>(x + t * xstride + kb * 128 + c.lane * 4);
+            xv[t][0] = a.x; xv[t][1] = a.y; xv[t][2] = a.z; xv[t][3] = a.w;
+          }
+        }
+#pragma unroll
+        for (int sl = 0; sl < 2; ++sl) {
+          const int p = c.warp + NCW * sl;
+          if (p < npairs) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const int r = 2 * p + h;
+              const uint4 w = *reinterpret_cast<const uint4*>(tile + ((size_t)(r * m + j) * 32 + c.lane) * 16);
+              float wf[EPL];
+              if constexpr (BF) {
+                wf[0] = bf_lo(w.x); wf[1] = bf_hi(w.x); wf[2] = bf_lo(w.y); wf[3] = bf_hi(w.y);
+                wf[4] = bf_lo(w.z); wf[5] = bf_hi(w.z); wf[6] = bf_lo(w.w); wf[7] = bf_hi(w.w);
+              } else {
+                wf[0] = __uint_as_float(w.x); wf[1] = __uint_as_float(w.y);
+                wf[2] = __uint_as_float(w.z); wf[3] = __uint_as_float(w.w);
+              }
+#pragma unroll
+              for (int t = 0; t < NT; ++t)
+#pragma unroll
+                for (int e = 0; e < EPL; ++e) acc[sl * 2 + h][t] = fmaf(wf[e], xv[t][e], acc[sl * 2 + h][t]);
+            }
+          }
+        }
+      }
+      __syncwarp();
+      if (c.lane == 0) mbar_arrive(&c.s.empty[stage]);
+      c.tile_ctr++;
+    }
+#pragma unroll
+    for (int sl = 0; sl < 2; ++sl) {
+      const int p = c.warp + NCW * sl;
+      if (p < npairs) {
+        float v0[NT], v1[NT];
+#pragma unroll
+        for (int t = 0; t < NT; ++t) {
+          float a = acc[sl * 2][t], b = acc[sl * 2 + 1][t];
+#pragma unroll
+          for (int o = 16; o; o >>= 1) {
+            a += __shfl_xor_sync(0xffffffffu, a, o);
+            b += __shfl_xor_sync(0xffffffffu, b, o);
+          }
+          v0[t] = a;
+          v1[t] = b;
+        }
+        if (c.lane == 0) epi(g.row0 + 2 * p, v0, v1);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Producer: stream the segments of the program in consumption order.
+// ------------------------------------------------------------------------------------------------------------
+struct Producer {
+  const KParams& P;
+  Smem& s;
+  uint32_t ctr;
+  bool stopped;
+  __device__ __forceinline__ void seg(int sg) {
+    if (stopped) return;
+    const uint32_t st = s.seg[sg];
+    const int gbeg = (int)(st >> 8), gn = (int)(st & 255u);
+    for (int gi = 0; gi < gn; ++gi) {
+      const Grp g = s.grp[gbeg + gi];
+      const uint32_t bytes = (uint32_t)g.rows * g.m * 512u;
+      const uint8_t* src = P.tape + (size_t)g.off16 * 16;
+      for (int tl = 0; tl < g.ntiles; ++tl) {
+        const int stage = (int)(ctr % NS);
+        const uint32_t par = ((ctr / NS) & 1u) ^ 1u;
+        while (!mbar_try_wait(&s.empty[stage], par)) {
+          if (s.stop_flag) {
+            stopped = true;
+            return;
+          }
+        }
+        if (s.stop_flag) {
+          stopped = true;
+          return;
+        }
+        mbar_expect_tx(&s.full[stage], bytes);
+        bulk_g2s(s.ring[stage], src + (size_t)tl * bytes, bytes, &s.full[stage]);
+        ++ctr;
+      }
+    }
+  }
+  __device__ __forceinline__ void stack_layers(const StackDev& S) {
+    for (int l = 0; l < S.L; ++l)
+      for (int q = 0; q < 4; ++q) seg(S.seg_base + 4 * l + q);
+  }
+};
+
+// ------------------------------------------------------------------------------------------------------------
+// Attention for one q-head over the KV cache (transformers eager_attention_forward semantics, GQA by repeat_kv).
+// nt tokens (1, or 2 for the predictor prefill), cache slots slot0.., rotary positions rpos0...
+// Also applies q_norm/k_norm + RoPE to the new q/k and appends K,V to the cache (talker_graph StaticCache.update).
+// ------------------------------------------------------------------------------------------------------------
+template <bool BF>
+__device__ void attention_head(Ctx& c, const StackDev& S, int layer, int h, int nt, int slot0, int rpos0,
+                               int kv_start) {
+  const KParams& P = c.P;
+  float* sc = c.s.xs;                // scores: [nt][scw]
+  const int scw = (nt == 1) ? SEQMAX : 32;
+  float* qs = c.s.xs + SEQMAX;       // [2][128]
+  float* ks = qs + 256;              // [2][128]
+  float* vs = ks + 256;              // [2][128]
+  float* opart = vs + 256;           // [8][128]
+  const int g = h / S.rep;
+  const size_t esz = BF ? 2 : 4;
+  const size_t head_stride = (size_t)S.S * 128;
+  uint8_t* kbase = reinterpret_cast<uint8_t*>(S.kc) + ((size_t)(layer * S.nKV + g) * head_stride) * esz;
+  uint8_t* vbase = reinterpret_cast<uint8_t*>(S.vc) + ((size_t)(layer * S.nKV + g) * head_stride) * esz;
+
+  // --- a. q/k norm + rope, v copy.  warp 3*t + {0:q,1:k,2:v}; lane owns e, e+32, e+64, e+96
+  if (c.warp < 3 * nt) {
+    const int t = c.warp / 3, what = c.warp % 3;
+    const float* src = P.QKV + (size_t)t * P.ldQKV + (what == 0 ? h * 128 : (what == 1 ? S.qd + g * 128 : S.qd + S.kd + g * 128));
+    float v[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] = __ldcg(src + c.lane + 32 * i);
+    if (what < 2) {
+      float ss = v[0] * v[0] + v[1] * v[1] + v[2] * v[2] + v[3] * v[3];
+#pragma unroll
+      for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+      const float r = 1.0f / sqrtf(ss / 128.0f + S.eps);
+      const void* nw = what == 0 ? S.qnorm : S.knorm;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) v[i] = rnd<BF>(ldw<BF>(nw, (size_t)layer * 128 + c.lane + 32 * i) * rnd<BF>(v[i] * r));
+      int rp = rpos0 + t;
+      rp = rp < 0 ? 0 : (rp >= S.npos ? S.npos - 1 : rp);
+      const float* cs = S.cos + (size_t)rp * 128;
+      const float* sn = S.sin + (size_t)rp * 128;
+      float o[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int e = c.lane + 32 * i;
+        const float cc = rnd<BF>(__ldg(cs + e)), sv = rnd<BF>(__ldg(sn + e));
+        const float rot = (i < 2) ? -v[i + 2] : v[i - 2];
+        o[i] = rnd<BF>(rnd<BF>(v[i] * cc) + rnd<BF>(rot * sv));
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) v[i] = o[i];
+    }
+    float* dst = (what == 0 ? qs : (what == 1 ? ks : vs)) + t * 128;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) dst[c.lane + 32 * i] = v[i];
+    if (what > 0 && (h % S.rep) == 0) {
+      uint8_t* cb = (what == 1 ? kbase : vbase) + (size_t)(slot0 + t) * 128 * esz;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) stw<BF>(cb, c.lane + 32 * i, v[i]);
+    }
+  }
+  csync();
+
+  const float scale = 0.08838834764831845f;  // 128^-0.5
+  for (int t = 0; t < nt; ++t) {
+    const int last = slot0 + t;          // newest key slot visible to token t
+    const int nk = last + 1 - kv_start;  // number of visible keys
+    const int nold = slot0 - kv_start;   // keys that live in the global cache
+    float* sct = sc + t * scw;
+    // --- b. scores
+    {
+      constexpr int LPK = BF ? 16 : 32;  // lanes per key (16 bytes per lane)
+      constexpr int KPW = 32 / LPK;      // keys per warp-instruction
+      constexpr int EPL = BF ? 8 : 4;
+      constexpr int U = 8;
+      const int sub = c.lane % LPK, kin = c.lane / LPK;
+      float q[EPL];
+#pragma unroll
+      for (int e = 0; e < EPL; ++e) q[e] = qs[t * 128 + sub * EPL + e];
+      for (int base = 0; base < nold; base += NCW * KPW * U) {
+        uint4 kv[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int jj = base + (u * NCW + c.warp) * KPW + kin;
+          if (jj < nold)
+            kv[u] = __ldcg(reinterpret_cast<const uint4*>(kbase + ((size_t)(kv_start + jj) * 128) * esz) + sub);
+          else
+            kv[u] = make_uint4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int jj = base + (u * NCW + c.warp) * KPW + kin;
+          float d = 0.f;
+          if constexpr (BF) {
+            d = fmaf(q[0], bf_lo(kv[u].x), d); d = fmaf(q[1], bf_hi(kv[u].x), d);
+            d = fmaf(q[2], bf_lo(kv[u].y), d); d = fmaf(q[3], bf_hi(kv[u].y), d);
+            d = fmaf(q[4], bf_lo(kv[u].z), d); d = fmaf(q[5], bf_hi(kv[u].z), d);
+            d = fmaf(q[6], bf_lo(kv[u].w), d); d = fmaf(q[7], bf_hi(kv[u].w), d);
+          } else {
+            d = fmaf(q[0], __uint_as_float(kv[u].x), d); d = fmaf(q[1], __uint_as_float(kv[u].y), d);
+            d = fmaf(q[2], __uint_as_float(kv[u].z), d); d = fmaf(q[3], __uint_as_float(kv[u].w), d);
+          }
+#pragma unroll
+          for (int o = LPK / 2; o; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+          if (sub == 0 && jj < nold) sct[jj] = rnd<BF>(rnd<BF>(d) * scale);
+        }
+      }
+      // new keys (held in shared memory): warp 0, one key per iteration
+      if (c.warp == 0) {
+        for (int j = 0; j <= t; ++j) {
+          float d = 0.f;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) d = fmaf(qs[t * 128 + c.lane + 32 * i], ks[j * 128 + c.lane + 32 * i], d);
+#pragma unroll
+          for (int o = 16; o; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+          if (c.lane == 0) sct[nold + j] = rnd<BF>(rnd<BF>(d) * scale);
+        }
+      }
+    }
+    csync();
+    // --- c. softmax (fp32, then rounded to dtype like softmax(..., dtype=float32).to(q.dtype))
+    float mx = -INFINITY;
+    for (int j = c.tid; j < nk; j += NCT) mx = fmaxf(mx, sct[j]);
+    mx = block_max(c, mx);
+    float sm = 0.f;
+    for (int j = c.tid; j < nk; j += NCT) {
+      const float e = expf(sct[j] - mx);
+      sct[j] = e;
+      sm += e;
+    }
+    sm = block_sum(c, sm);
+    for (int j = c.tid; j < nk; j += NCT) sct[j] = rnd<BF>(sct[j] / sm);
+    csync();
+    // --- d. P.V : warp w takes keys w, w+8, ...; lane owns dims [4*lane, 4*lane+4)
+    {
+      constexpr int U = 8;
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+      for (int base = c.warp; base < nold; base += NCW * U) {
+        float pv[U];
+        uint4 vv[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int jj = base + u * NCW;
+          if (jj < nold) {
+            const uint8_t* row = vbase + ((size_t)(kv_start + jj) * 128) * esz;
+            if constexpr (BF) {
+              const uint2 w2 = __ldcg(reinterpret_cast<const uint2*>(row) + c.lane);
+              vv[u] = make_uint4(w2.x, w2.y, 0, 0);
+            } else {
+              vv[u] = __ldcg(reinterpret_cast<const uint4*>(row) + c.lane);
+            }
+            pv[u] = sct[jj];
+          } else {
+            vv[u] = make_uint4(0, 0, 0, 0);
+            pv[u] = 0.f;
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          if constexpr (BF) {
+            a0 = fmaf(pv[u], bf_lo(vv[u].x), a0); a1 = fmaf(pv[u], bf_hi(vv[u].x), a1);
+            a2 = fmaf(pv[u], bf_lo(vv[u].y), a2); a3 = fmaf(pv[u], bf_hi(vv[u].y), a3);
+          } else {
+            a0 = fmaf(pv[u], __uint_as_float(vv[u].x), a0); a1 = fmaf(pv[u], __uint_as_float(vv[u].y), a1);
+            a2 = fmaf(pv[u], __uint_as_float(vv[u].z), a2); a3 = fmaf(pv[u], __uint_as_float(vv[u].w), a3);
+          }
+        }
+      }
+      if (c.warp == 0) {
+        for (int j = 0; j <= t; ++j) {
+          const float pj = sct[nold + j];
+          a0 = fmaf(pj, vs[j * 128 + 4 * c.lane + 0], a0);
+          a1 = fmaf(pj, vs[j * 128 + 4 * c.lane + 1], a1);
+          a2 = fmaf(pj, vs[j * 128 + 4 * c.lane + 2], a2);
+          a3 = fmaf(pj, vs[j * 128 + 4 * c.lane + 3], a3);
+        }
+      }
+      float* op = opart + c.warp * 128 + 4 * c.lane;
+      op[0] = a0; op[1] = a1; op[2] = a2; op[3] = a3;
+    }
+    csync();
+    if (c.tid < 128) {
+      float o = 0.f;
+#pragma unroll
+      for (int w = 0; w < NCW; ++w) o += opart[w * 128 + c.tid];
+      P.ATT[(size_t)t * P.ldATT + h * 128 + c.tid] = rnd<BF>(o);
+    }
+    csync();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Sampling (sampling.py:32-66 + :10-29), computed redundantly and deterministically by every CTA.
+// Returns the token to all consumer threads.
+// ------------------------------------------------------------------------------------------------------------
+struct SampleArgs {
+  const float* logits;  // global fp32 (dtype-rounded values)
+  int V;
+  Sampling sp;
+  float u;
+  bool use_penalty;     // repetition penalty over the seen bitmap
+  int sup0;             // ids in [sup0, V) except eos are suppressed (V = none)   generate.py:46-50
+  bool suppress_eos;
+  int eos;
+};
+
+__device__ __forceinline__ uint32_t fkey(float f) {  // order-preserving float -> uint
+  const uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float fkey_inv(uint32_t k) {
+  return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
+template <bool BF>
+__device__ int sample_block(Ctx& c, const SampleArgs& a) {
+  float* lg = c.s.xs;  // [V]
+  const int V = a.V;
+  const int sup0 = a.sup0;
+  for (int v = c.tid; v < V; v += NCT) {
+    float l = __ldcg(a.logits + v);
+    if (a.use_penalty && a.sp.penalty != 1.0f && ((c.s.seen[v >> 5] >> (v & 31)) & 1u))
+      l = l > 0.f ? rnd<BF>(l / a.sp.penalty) : rnd<BF>(l * a.sp.penalty);
+    if ((v >= sup0 && v != a.eos) || (a.suppress_eos && v == a.eos)) l = -INFINITY;
+    lg[v] = l;
+  }
+  csync();
+  if (!a.sp.do_sample) {  // argmax, lowest index among maxima
+    float bm = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int v = c.tid; v < V; v += NCT) {
+      const float l = lg[v];
+      if (l > bm || (l == bm && v < bi)) { bm = l; bi = v; }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      const float om = __shfl_xor_sync(0xffffffffu, bm, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (om > bm || (om == bm && oi < bi)) { bm = om; bi = oi; }
+    }
+    if (c.lane == 0) { c.s.red[c.warp] = bm; c.s.hist[c.warp] = bi; }
+    csync();
+    float m = c.s.red[0];
+    int bi2 = c.s.hist[0];
+    for (int w = 1; w < NCW; ++w) {
+      const float om = c.s.red[w];
+      const int oi = c.s.hist[w];
+      if (om > m || (om == m && oi < bi2)) { m = om; bi2 = oi; }
+    }
+    csync();
+    return bi2;
+  }
+  // temperature
+  for (int v = c.tid; v < V; v += NCT) lg[v] = rnd<BF>(lg[v] / a.sp.temperature);
+  csync();
+  // top-k with ties kept: threshold = k-th largest value (sampling.py:54-56)
+  if (a.sp.top_k > 0 && a.sp.top_k < V) {
+    uint32_t prefix = 0, mask = 0;
+    int remaining = a.sp.top_k;
+    for (int pass = 0; pass < 4; ++pass) {
+      const int shift = 24 - 8 * pass;
+      c.s.hist[c.tid] = 0;
+      csync();
+      for (int v = c.tid; v < V; v += NCT) {
+        const uint32_t k = fkey(lg[v]);
+        if ((k & mask) == prefix) atomicAdd(&c.s.hist[(k >> shift) & 255u], 1);
+      }
+      csync();
+      if (c.warp == 0) {  // lane L owns bins 255-8L .. 248-8L (descending)
+        int cnt[8], tot = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { cnt[i] = c.s.hist[255 - 8 * c.lane - i]; tot += cnt[i]; }
+        int incl = tot;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int n = __shfl_up_sync(0xffffffffu, incl, o);
+          if (c.lane >= o) incl += n;
+        }
+        const int excl = incl - tot;
+        if (excl < remaining && incl >= remaining) {
+          int run = excl;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            if (run < remaining && run + cnt[i] >= remaining) {
+              c.s.ibc[0] = 255 - 8 * c.lane - i;
+              c.s.ibc[1] = remaining - run;
+            }
+            run += cnt[i];
+          }
+        }
+      }
+      csync();
+      prefix |= ((uint32_t)c.s.ibc[0]) << shift;
+      mask |= 255u << shift;
+      remaining = c.s.ibc[1];
+      csync();
+    }
+    const float kth = fkey_inv(prefix);
+    for (int v = c.tid; v < V; v += NCT)
+      if (lg[v] < kth) lg[v] = -INFINITY;
+    csync();
+  }
+  // top-p (fp32 semantics, order: value desc then index asc; keep position 0 and every position with cum <= top_p)
+  if (a.sp.top_p < 1.0f) {
+    float* sl = &c.s.xin[0][0];                                      // sorted values [V] (xin is free here)
+    uint16_t* rk = reinterpret_cast<uint16_t*>(c.s.xs + VMAX);       // ranks [V]
+    for (int v = c.tid; v < V; v += NCT) {
+      const float l = lg[v];
+      int r = 0;
+      for (int w = 0; w < V; ++w) {
+        const float o = lg[w];
+        r += (o > l || (o == l && w < v)) ? 1 : 0;
+      }
+      rk[v] = (uint16_t)r;
+      sl[r] = l;
+    }
+    csync();
+    if (c.tid == 0) {
+      const float m0 = sl[0];
+      float S = 0.f;
+      for (int i = 0; i < V; ++i) S += expf(sl[i] - m0);
+      float cum = 0.f;
+      int keep = 1;
+      for (int i = 0; i < V; ++i) {
+        cum += expf(sl[i] - m0) / S;
+        if (i > 0 && !(cum > a.sp.top_p)) keep = i + 1;
+        if (cum > a.sp.top_p && i > 0) break;
+      }
+      c.s.ibc[2] = keep;
+    }
+    csync();
+    const int keep = c.s.ibc[2];
+    for (int v = c.tid; v < V; v += NCT)
+      if ((int)rk[v] >= keep) lg[v] = -INFINITY;
+    csync();
+  }
+  // softmax -> probabilities in model dtype (F.softmax on a dtype tensor)
+  float mx = -INFINITY;
+  for (int v = c.tid; v < V; v += NCT) mx = fmaxf(mx, lg[v]);
+  mx = block_max(c, mx);
+  float sm = 0.f;
+  for (int v = c.tid; v < V; v += NCT) {
+    const float e = expf(lg[v] - mx);
+    lg[v] = e;
+    sm += e;
+  }
+  sm = block_sum(c, sm);
+  for (int v = c.tid; v < V; v += NCT) lg[v] = rnd<BF>(lg[v] / sm);
+  csync();
+  // inverse-CDF draw, summation order fixed (oracle/qwen3_tts_oracle.py draw_inverse_cdf)
+  const int CH = (V + NCT - 1) / NCT;
+  float cs = 0.f;
+  for (int j = 0; j < CH; ++j) {
+    const int idx = c.tid * CH + j;
+    if (idx < V) cs += lg[idx];
+  }
+  float incl = cs;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const float n = __shfl_up_sync(0xffffffffu, incl, o);
+    if (c.lane >= o) incl += n;
+  }
+  if (c.lane == 31) c.s.red[c.warp] = incl;
+  if (c.tid == 0) {
+    c.s.ibc[3] = -1;
+    c.s.ibc[0] = 0x7fffffff;
+  }
+  csync();
+  float woff = 0.f, total = 0.f;
+  for (int w = 0; w < NCW; ++w) {
+    if (w == c.warp) woff = total;
+    total += c.s.red[w];
+  }
+  incl += woff;
+  const float target = a.u * total;
+  float excl = __shfl_up_sync(0xffffffffu, incl, 1);
+  if (c.lane == 0) excl = woff;
+  // lowest chunk whose inclusive prefix exceeds the target (prefix sums need not be monotone in fp32; the
+  // oracle takes the first such chunk too)
+  const bool hit = incl > target;
+  if (hit) atomicMin(&c.s.ibc[0], c.tid);
+  csync();
+  if (hit && c.s.ibc[0] == c.tid) {
+    float run = excl;
+    int pick = -1;
+    for (int j = 0; j < CH; ++j) {
+      const int idx = c.tid * CH + j;
+      if (idx >= V) break;
+      run += lg[idx];
+      if (run > target && lg[idx] > 0.f) { pick = idx; break; }
+    }
+    c.s.ibc[3] = pick;
+  }
+  csync();
+  int tok = c.s.ibc[3];
+  if (tok < 0) {  // rounding left nothing selected: last index with p > 0
+    int best = -1;
+    for (int v = c.tid; v < V; v += NCT)
+      if (lg[v] > 0.f) best = v > best ? v : best;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, o));
+    if (c.lane == 0) c.s.hist[c.warp] = best;
+    csync();
+    tok = c.s.hist[0];
+    for (int w = 1; w < NCW; ++w) tok = max(tok, c.s.hist[w]);
+    if (tok < 0) tok = 0;
+  }
+  csync();
+  return tok;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// One pass through a transformer stack for nt tokens held in X (global) or xin (shared, layer 0).
+// On return every CTA holds the final-norm hidden of the LAST token in s.xs[0..H) and X holds the residual stream.
+// ------------------------------------------------------------------------------------------------------------
+template <bool BF>
+__device__ void run_layers(Ctx& c, const StackDev& S, int nt, int slot0, int rpos0, int kv_start, bool x0_local,
+                           bool dbg, bool is_talker) {
+  const KParams& P = c.P;
+  const bool cta0 = blockIdx.x == 0;
+  for (int l = 0; l < S.L; ++l) {
+    // ---- P1: input norm + QKV rows
+    for (int t = 0; t < nt; ++t) {
+      if (l == 0 && x0_local)
+        norm_smem_to_smem<BF>(c, c.s.xin[t], S.ln_in, (size_t)l * S.H, S.H, S.eps, c.s.xs + t * S.H);
+      else
+        norm_to_smem<BF>(c, P.X + (size_t)t * P.ldX, S.ln_in, (size_t)l * S.H, S.H, S.eps, c.s.xs + t * S.H);
+    }
+    {
+      auto epi = [&](int row, const float* v0, const float* v1) {
+        for (int t = 0; t < nt; ++t) {
+          P.QKV[(size_t)t * P.ldQKV + row] = rnd<BF>(v0[t]);
+          P.QKV[(size_t)t * P.ldQKV + row + 1] = rnd<BF>(v1[t]);
+        }
+      };
+      if (nt == 1) gemv_seg<BF, 1>(c, S.seg_base + 4 * l + 0, c.s.xs, S.H, epi);
+      else gemv_seg<BF, 2>(c, S.seg_base + 4 * l + 0, c.s.xs, S.H, epi);
+    }
+    grid_sync(c);
+    if (dbg && cta0) {
+      float* d = P.dbg + (size_t)l * P.dbg_stride_layer;
+      for (int t = 0; t < nt; ++t)
+        for (int k = c.tid; k < S.qd + 2 * S.kd; k += NCT) d[(size_t)t * (S.qd + 2 * S.kd) + k] = __ldcg(P.QKV + (size_t)t * P.ldQKV + k);
+    }
+    // ---- P2: attention, one q-head per CTA
+    for (int h = blockIdx.x; h < S.nH; h += gridDim.x) attention_head<BF>(c, S, l, h, nt, slot0, rpos0, kv_start);
+    grid_sync(c);
+    // ---- P3: o_proj + residual
+    for (int t = 0; t < nt; ++t)
+      for (int k = c.tid; k < S.qd; k += NCT) c.s.xs[t * S.qd + k] = __ldcg(P.ATT + (size_t)t * P.ldATT + k);
+    csync();
+    if (dbg && cta0) {
+      float* d = P.dbg + (size_t)l * P.dbg_stride_layer + (size_t)2 * (S.qd + 2 * S.kd);
+      for (int k = c.tid; k < nt * S.qd; k += NCT) d[k] = c.s.xs[k];
+    }
+    {
+      const bool loc = (l == 0 && x0_local);
+      auto epi = [&](int row, const float* v0, const float* v1) {
+        for (int t = 0; t < nt; ++t) {
+          const float r0 = loc ? c.s.xin[t][row] : __ldcg(P.X + (size_t)t * P.ldX + row);
+          const float r1 = loc ? c.s.xin[t][row + 1] : __ldcg(P.X + (size_t)t * P.ldX + row + 1);
+          P.X1[(size_t)t * P.ldX + row] = rnd<BF>(r0 + rnd<BF>(v0[t]));
+          P.X1[(size_t)t * P.ldX + row + 1] = rnd<BF>(r1 + rnd<BF>(v1[t]));
+        }
+      };
+      if (nt == 1) gemv_seg<BF, 1>(c, S.seg_base + 4 * l + 1, c.s.xs, S.qd, epi);
+      else gemv_seg<BF, 2>(c, S.seg_base + 4 * l + 1, c.s.xs, S.qd, epi);
+    }
+    grid_sync(c);
+    // ---- P4: post-attention norm + gate/up rows (interleaved pairs) + SiLU*up
+    for (int t = 0; t < nt; ++t)
+      norm_to_smem<BF>(c, P.X1 + (size_t)t * P.ldX, S.ln_post, (size_t)l * S.H, S.H, S.eps, c.s.xs + t * S.H);
+    if (dbg && cta0) {
+      float* d = P.dbg + (size_t)l * P.dbg_stride_layer + (size_t)2 * (S.qd + 2 * S.kd) + 2 * S.qd;
+      for (int t = 0; t < nt; ++t)
+        for (int k = c.tid; k < S.H; k += NCT) d[(size_t)t * S.H + k] = __ldcg(P.X1 + (size_t)t * P.ldX + k);
+    }
+    {
+      auto epi = [&](int row, const float* v0, const float* v1) {
+        for (int t = 0; t < nt; ++t) {
+          const float gte = rnd<BF>(v0[t]), up = rnd<BF>(v1[t]);
+          const float sl = rnd<BF>(gte / (1.0f + expf(-gte)));
+          P.ACT[(size_t)t * P.ldACT + (row >> 1)] = rnd<BF>(sl * up);
+        }
+      };
+      if (nt == 1) gemv_seg<BF, 1>(c, S.seg_base + 4 * l + 2, c.s.xs, S.H, epi);
+      else gemv_seg<BF, 2>(c, S.seg_base + 4 * l + 2, c.s.xs, S.H, epi);
+    }
+    grid_sync(c);
+    // ---- P5: down rows + residual
+    for (int t = 0; t < nt; ++t)
+      for (int k = c.tid; k < S.I; k += NCT) c.s.xs[t * S.I + k] = __ldcg(P.ACT + (size_t)t * P.ldACT + k);
+    csync();
+    if (dbg && cta0) {
+      float* d = P.dbg + (size_t)l * P.dbg_stride_layer + (size_t)2 * (S.qd + 2 * S.kd) + 2 * S.qd + 2 * S.H;
+      for (int k = c.tid; k < nt * S.I; k += NCT) d[k] = c.s.xs[k];
+    }
+    {
+      auto epi = [&](int row, const float* v0, const float* v1) {
+        for (int t = 0; t < nt; ++t) {
+          const float r0 = __ldcg(P.X1 + (size_t)t * P.ldX + row), r1 = __ldcg(P.X1 + (size_t)t * P.ldX + row + 1);
+          P.X[(size_t)t * P.ldX + row] = rnd<BF>(r0 + rnd<BF>(v0[t]));
+          P.X[(size_t)t * P.ldX + row + 1] = rnd<BF>(r1 + rnd<BF>(v1[t]));
+        }
+      };
+      if (nt == 1) gemv_seg<BF, 1>(c, S.seg_base + 4 * l + 3, c.s.xs, S.I, epi);
+      else gemv_seg<BF, 2>(c, S.seg_base + 4 * l + 3, c.s.xs, S.I, epi);
+    }
+    grid_sync(c);
+    if (dbg && cta0) {
+      float* d = P.dbg + (size_t)l * P.dbg_stride_layer + (size_t)2 * (S.qd + 2 * S.kd) + 2 * S.qd + 2 * S.H + 2 * S.I;
+      for (int t = 0; t < nt; ++t)
+        for (int k = c.tid; k < S.H; k += NCT) d[(size_t)t * S.H + k] = __ldcg(P.X + (size_t)t * P.ldX + k);
+    }
+  }
+  // final norm of the last token -> xs[0..H)
+  norm_to_smem<BF>(c, P.X + (size_t)(nt - 1) * P.ldX, S.ln_f, 0, S.H, S.eps, c.s.xs);
+  (void)is_talker;
+}
+
+// head GEMV (rows of a [V,H] matrix) on xs[0..H) -> LOGITS, then grid barrier
+template <bool BF>
+__device__ __forceinline__ void head_logits(Ctx& c, int seg, int H) {
+  const KParams& P = c.P;
+  auto epi = [&](int row, const float* v0, const float* v1) {
+    P.LOGITS[row] = rnd<BF>(v0[0]);
+    P.LOGITS[row + 1] = rnd<BF>(v1[0]);
+  };
+  gemv_seg<BF, 1>(c, seg, c.s.xs, H, epi);
+  grid_sync(c);
+}
+
+// predictor: 15 passes (predictor_graph.py:115-167).  Inputs: s.xin[0] = past_hidden, s.xin[1] = embed(cb0 token).
+// Outputs s.codes[1..15].  u15: 15 uniforms.
+template <bool BF>
+__device__ void predictor_frame(Ctx& c, const float* u15, bool dbg) {
+  const KParams& P = c.P;
+  const StackDev& S = P.p;
+  const int Ht = P.t.H;
+  const bool cta0 = blockIdx.x == 0;
+  for (int i = 0; i < P.ncb; ++i) {
+    const int nt = (i == 0) ? 2 : 1;
+    if (i > 0) {
+      const int prev = c.s.codes[i];  // code sampled by pass i-1
+      for (int k = c.tid; k < Ht; k += NCT)
+        c.s.xin[0][k] = ldw<BF>(P.p_embeds, ((size_t)(i - 1) * S.V + prev) * Ht + k);
+      csync();
+    }
+    bool x0_local;
+    if (P.has_mtp) {
+      auto epi = [&](int row, const float* v0, const float* v1) {
+        const float b0 = P.mtp_b ? ldw<BF>(P.mtp_b, row) : 0.f, b1 = P.mtp_b ? ldw<BF>(P.mtp_b, row + 1) : 0.f;
+        for (int t = 0; t < nt; ++t) {
+          P.X[(size_t)t * P.ldX + row] = rnd<BF>(v0[t] + b0);
+          P.X[(size_t)t * P.ldX + row + 1] = rnd<BF>(v1[t] + b1);
+        }
+      };
+      if (nt == 1) gemv_seg<BF, 1>(c, P.seg_mtp, &c.s.xin[0][0], HMAX, epi);
+      else gemv_seg<BF, 2>(c, P.seg_mtp, &c.s.xin[0][0], HMAX, epi);
+      grid_sync(c);
+      x0_local = false;
+    } else {
+      x0_local = true;
+    }
+    const int slot0 = (i == 0) ? 0 : i + 1;
+    run_layers<BF>(c, S, nt, slot0, slot0, 0, x0_local, dbg && i == 0, false);
+    head_logits<BF>(c, S.seg_head + i, S.H);
+    SampleArgs sa;
+    sa.logits = P.LOGITS; sa.V = S.V; sa.sp = P.sp_p; sa.u = u15 ? __ldg(u15 + i) : 0.f;
+    sa.use_penalty = false; sa.sup0 = S.V; sa.suppress_eos = false; sa.eos = -1;
+    const int tok = sample_block<BF>(c, sa);
+    if (c.tid == 0) c.s.codes[i + 1] = tok;
+    csync();
+    (void)cta0;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// the kernel
+// ------------------------------------------------------------------------------------------------------------
+template <bool BF>
+__global__ void __launch_bounds__(NTHREADS, 1) fq3_decode_kernel(const __grid_constant__ KParams P) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  Smem& s = *reinterpret_cast<Smem*>(smem_raw);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int cta = blockIdx.x;
+
+  // one-time setup: per-CTA group / segment tables, barriers
+  {
+    const uint32_t g0 = __ldg(P.cta_grp_off + cta), g1 = __ldg(P.cta_grp_off + cta + 1);
+    for (uint32_t i = tid; i < g1 - g0; i += NTHREADS) s.grp[i] = P.grps[g0 + i];
+    for (int i = tid; i < P.nseg; i += NTHREADS) s.seg[i] = __ldg(P.segtab + (size_t)cta * P.nseg + i);
+    for (int i = tid; i < VMAX / 32; i += NTHREADS) s.seen[i] = P.mode == MODE_FUSED ? P.seen[i] : 0u;
+    if (tid == 0) {
+      for (int i = 0; i < NS; ++i) {
+        mbar_init(&s.full[i], 1);
+        mbar_init(&s.empty[i], NCW);
+      }
+      s.stop_flag = 0;
+      s.prod_done = 0;
+      s.prod_issued = 0;
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+  }
+  __syncthreads();
+
+  if (warp == NCW) {
+    // ======================================= PRODUCER =======================================
+    if (lane == 0) {
+      Producer pr{P, s, 0u, false};
+      if (P.mode == MODE_TALKER_STEP) {
+        pr.stack_layers(P.t);
+      } else {
+        const int iters = P.mode == MODE_FUSED ? P.n_frames : 1;
+        for (int f = 0; f < iters && !pr.stopped; ++f) {
+          for (int i = 0; i < P.ncb; ++i) {
+            if (P.has_mtp) pr.seg(P.seg_mtp);
+            pr.stack_layers(P.p);
+            pr.seg(P.p.seg_head + i);
+          }
+          if (P.mode == MODE_FUSED) {
+            pr.stack_layers(P.t);
+            pr.seg(P.t.seg_head);
+          }
+        }
+      }
+      s.prod_issued = (int)pr.ctr;
+      __threadfence_block();
+      s.prod_done = 1;
+    }
+  } else {
+    // ======================================= CONSUMERS ======================================
+    Ctx c{P, s, tid, warp, lane, 0u, 0u};
+    const int Ht = P.t.H;
+    if (P.mode == MODE_TALKER_STEP) {
+      for (int k = tid; k < Ht; k += NCT) s.xin[0][k] = ldw<BF>(P.in_embeds, k);
+      csync();
+      run_layers<BF>(c, P.t, 1, P.position, P.position + P.rope_delta, P.n_left_pad, true, P.dbg_on != 0, true);
+      if (cta == 0)
+        for (int k = tid; k < Ht; k += NCT) stw<BF>(P.hidden_out, k, s.xs[k]);
+    } else if (P.mode == MODE_PRED_RUN) {
+      for (int k = tid; k < 2 * Ht; k += NCT) s.xin[k / Ht][k % Ht] = ldw<BF>(P.pred_input, k);
+      csync();
+      predictor_frame<BF>(c, P.sp_p.do_sample ? P.pred_uniforms : nullptr, P.dbg_on != 0);
+      if (cta == 0 && tid < P.ncb) P.codes_out[tid] = (long long)s.codes[tid + 1];
+    } else {
+      // ---------------- fused frame loop: generate.py:149-199 / streaming.py:106-173 ----------------
+      int token = P.state[0], step = P.state[1], gen_step = P.state[2];
+      int finished = 0, emitted = 0;
+      for (int k = tid; k < Ht; k += NCT) s.hid[k] = P.past_hidden[k];
+      csync();
+      while (true) {
+        if (emitted >= P.n_frames) break;
+        if (step >= P.max_new) { finished = 1; break; }
+        if (token == P.eos) { finished = 2; break; }
+        // predictor input: cat(past_hidden, codec_embedding(token))   generate.py:154-155
+        for (int k = tid; k < Ht; k += NCT) {
+          s.xin[0][k] = s.hid[k];
+          s.xin[1][k] = ldw<BF>(P.t_embed, (size_t)token * Ht + k);
+        }
+        if (tid == 0) {
+          s.codes[0] = token;
+          s.seen[token >> 5] |= 1u << (token & 31);
+        }
+        csync();
+        const float* urow = P.uniforms + (size_t)(step + 1) * 16;
+        predictor_frame<BF>(c, P.sp_p.do_sample ? urow + 1 : nullptr, false);
+        if (cta == 0 && tid < 16) P.codes_out[(size_t)emitted * 16 + tid] = (long long)s.codes[tid];
+        emitted++;
+        // next talker input: sum of 16 embedding rows + trailing text / tts_pad   generate.py:163-171
+        {
+          const void* extra = gen_step < P.trailing_len ? P.trailing : P.tts_pad;
+          const size_t eoff = gen_step < P.trailing_len ? (size_t)gen_step * Ht : 0;
+          for (int k = tid; k < Ht; k += NCT) {
+            float sm = ldw<BF>(P.t_embed, (size_t)token * Ht + k);
+            for (int i = 0; i < P.ncb; ++i) sm += ldw<BF>(P.p_embeds, ((size_t)i * P.p.V + s.codes[i + 1]) * Ht + k);
+            s.xin[0][k] = rnd<BF>(rnd<BF>(sm) + ldw<BF>(extra, eoff + k));
+          }
+          csync();
+        }
+        const int pos = P.prefill_len + step;
+        if (pos >= P.max_seq_len - 1) { finished = 3; step++; break; }   // generate.py:175-177 (frame already emitted)
+        run_layers<BF>(c, P.t, 1, pos, pos + P.rope_delta, P.n_left_pad, true, false, true);
+        for (int k = tid; k < Ht; k += NCT) s.hid[k] = s.xs[k];   // past_hidden = post-norm hidden (generate.py:198)
+        csync();
+        head_logits<BF>(c, P.t.seg_head, Ht);
+        SampleArgs sa;
+        sa.logits = P.LOGITS; sa.V = P.t.V; sa.sp = P.sp_t; sa.u = P.sp_t.do_sample ? __ldg(urow) : 0.f;
+        sa.use_penalty = true; sa.sup0 = P.t.V > 1024 ? P.t.V - 1024 : 0;
+        sa.suppress_eos = (step + 1) < P.min_new; sa.eos = P.eos;
+        token = sample_block<BF>(c, sa);
+        step++;
+        gen_step++;
+      }
+      if (cta == 0) {
+        if (tid == 0) {
+          P.state[0] = token; P.state[1] = step; P.state[2] = gen_step; P.state[3] = finished; P.state[4] = emitted;
+        }
+        for (int k = tid; k < Ht; k += NCT) P.past_hidden[k] = s.hid[k];
+        for (int i = tid; i < VMAX / 32; i += NCT) P.seen[i] = s.seen[i];
+      }
+    }
+    // ---- drain: stop the producer and wait for every bulk copy it has in flight
+    csync();
+    if (tid == 0) {
+      s.stop_flag = 1;
+      __threadfence_block();
+      while (!s.prod_done) {
+      }
+      __threadfence_block();
+      const uint32_t issued = (uint32_t)s.prod_issued;
+      for (uint32_t t = c.tile_ctr; t < issued; ++t) mbar_wait(&s.full[t % NS], (t / NS) & 1u);
+    }
+    csync();
+  }
+  __syncthreads();
+}
+
+}  // namespace fq3

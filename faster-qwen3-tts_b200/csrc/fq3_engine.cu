@@ -1,0 +1,703 @@
+// fq3_engine.cu -- C ABI implementation (see include/fq3_engine.h): engine lifecycle, weight-tape packing,
+// launches of the persistent decode kernel (fq3_decode.cuh).  sm_100a only.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/fq3_engine.h"
+#include "fq3_decode.cuh"
+
+using namespace fq3;
+
+// ------------------------------------------------------------------------------------------------------------
+static thread_local char g_err[1024] = "";
+static int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+#define CK(call)                                                                                         \
+  do {                                                                                                   \
+    cudaError_t _e = (call);                                                                             \
+    if (_e != cudaSuccess)                                                                               \
+      return fail(FQ3_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+struct SegHost {
+  int rows, K;
+  uint64_t bytes;  // total tape bytes of this segment (all CTAs)
+};
+
+struct PackGrp {
+  uint64_t tape_off;
+  uint32_t rowsrc_idx;
+  uint16_t rows, m, ntiles, pad;
+  int32_t K;
+};
+
+struct fq3_engine {
+  fq3_config cfg;
+  bool bf16;
+  size_t esz;
+  int ncta;
+  int dev;
+  bool loaded = false;
+  bool request_active = false;
+  // device buffers
+  void *t_kc = nullptr, *t_vc = nullptr, *p_kc = nullptr, *p_vc = nullptr;
+  float *X = nullptr, *X1 = nullptr, *QKV = nullptr, *ATT = nullptr, *ACT = nullptr, *LOGITS = nullptr;
+  unsigned* bar = nullptr;
+  int* state = nullptr;
+  int* state_host = nullptr;  // pinned
+  float* past_hidden = nullptr;
+  uint32_t* seen = nullptr;
+  float* dbg = nullptr;
+  size_t dbg_floats = 0;
+  long long dbg_stride = 0;
+  int dbg_on = 0;
+  uint8_t* tape = nullptr;
+  size_t tape_bytes = 0;
+  Grp* grps = nullptr;
+  uint32_t* segtab = nullptr;
+  uint32_t* cta_grp_off = nullptr;
+  std::map<std::string, void*> tabs;  // owned small tables (device)
+  std::vector<SegHost> segs;
+  int64_t talker_step_bytes = 0, predictor_frame_bytes = 0;
+  KParams kp;  // template parameters (static part)
+  int64_t launches = 0;
+};
+
+static size_t smem_bytes() { return sizeof(Smem); }
+
+// ------------------------------------------------------------------------------------------------------------
+// small kernels
+// ------------------------------------------------------------------------------------------------------------
+template <bool BF>
+__global__ void pack_kernel(const PackGrp* __restrict__ pg, int npg, const void* const* __restrict__ rowsrc,
+                            uint8_t* __restrict__ tape) {
+  for (int b = blockIdx.x; b < npg; b += gridDim.x) {
+    const PackGrp g = pg[b];
+    const int rows = g.rows, m = g.m;
+    const long long total = (long long)rows * m * g.ntiles * 32;
+    uint4* dst = reinterpret_cast<uint4*>(tape + g.tape_off);
+    for (long long q = threadIdx.x; q < total; q += blockDim.x) {
+      const int lane = (int)(q & 31);
+      long long rem = q >> 5;
+      const int j = (int)(rem % m);
+      rem /= m;
+      const int r = (int)(rem % rows);
+      const int t = (int)(rem / rows);
+      const int kb = t * m + j;
+      const uint8_t* src = reinterpret_cast<const uint8_t*>(rowsrc[g.rowsrc_idx + r]);
+      uint4 v;
+      if constexpr (BF) {
+        const uint2 a = *reinterpret_cast<const uint2*>(src + ((size_t)kb * 256 + lane * 4) * 2);
+        const uint2 c = *reinterpret_cast<const uint2*>(src + ((size_t)kb * 256 + 128 + lane * 4) * 2);
+        v = make_uint4(a.x, a.y, c.x, c.y);
+      } else {
+        v = *reinterpret_cast<const uint4*>(src + ((size_t)kb * 128 + lane * 4) * 4);
+      }
+      dst[q] = v;
+    }
+  }
+}
+
+template <bool BF>
+__global__ void set_state_kernel(int* state, float* past_hidden, uint32_t* seen, const void* ph_src, int Ht,
+                                 int token, int gen_step) {
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid == 0) {
+    state[0] = token; state[1] = 0; state[2] = gen_step; state[3] = 0; state[4] = 0;
+  }
+  for (int k = tid; k < Ht; k += gridDim.x * blockDim.x) past_hidden[k] = ldw<BF>(ph_src, k);
+  for (int k = tid; k < VMAX / 32; k += gridDim.x * blockDim.x) seen[k] = 0u;
+}
+
+template <bool BF>
+__global__ void get_hidden_kernel(const float* past_hidden, void* dst, int Ht) {
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < Ht; k += gridDim.x * blockDim.x) stw<BF>(dst, k, past_hidden[k]);
+}
+
+// standalone sampler: one CTA of 256 threads running the same sample_block the fused loop uses
+template <bool BF>
+__global__ void __launch_bounds__(NCT, 1)
+    sample_kernel(const __grid_constant__ KParams P, const void* logits, int V, Sampling sp, float u,
+                  const long long* hist, int n_hist, int suppress_special, int eos, int suppress_eos,
+                  long long* out) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  Smem& s = *reinterpret_cast<Smem*>(smem_raw);
+  const int tid = threadIdx.x;
+  for (int i = tid; i < VMAX / 32; i += NCT) s.seen[i] = 0u;
+  __syncthreads();
+  for (int i = tid; i < n_hist; i += NCT) {
+    const int v = (int)hist[i];
+    if (v >= 0 && v < V) atomicOr(&s.seen[v >> 5], 1u << (v & 31));
+  }
+  for (int v = tid; v < V; v += NCT) P.LOGITS[v] = ldw<BF>(logits, v);
+  __threadfence();
+  __syncthreads();
+  Ctx c{P, s, tid, tid >> 5, tid & 31, 0u, 0u};
+  SampleArgs a;
+  a.logits = P.LOGITS; a.V = V; a.sp = sp; a.u = u;
+  a.use_penalty = true;
+  a.sup0 = suppress_special ? (V > 1024 ? V - 1024 : 0) : V;
+  a.suppress_eos = suppress_eos != 0;
+  a.eos = eos;
+  const int tok = sample_block<BF>(c, a);
+  if (tid == 0) out[0] = tok;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// lifecycle
+// ------------------------------------------------------------------------------------------------------------
+static int check_stack(const fq3_stack_config& s, const char* nm, int nt) {
+  const int qd = s.num_attention_heads * 128, kd = s.num_key_value_heads * 128;
+  if (s.hidden_size <= 0 || s.hidden_size % 256 || s.intermediate_size % 256 || qd % 256 || kd % 128)
+    return fail(FQ3_ERR_INVALID, "%s: hidden/intermediate/q dims must be multiples of 256 (head_dim fixed at 128)", nm);
+  if (s.num_attention_heads % s.num_key_value_heads) return fail(FQ3_ERR_INVALID, "%s: heads %% kv_heads != 0", nm);
+  const int mx = std::max(std::max(s.hidden_size, qd), s.intermediate_size);
+  if (nt * mx > XS_FLOATS) return fail(FQ3_ERR_INVALID, "%s: %d x max(H,qd,I)=%d exceeds the %d-float staging buffer", nm, nt, mx, XS_FLOATS);
+  if (s.vocab_size > VMAX || s.vocab_size % 2) return fail(FQ3_ERR_INVALID, "%s: vocab_size must be even and <= %d", nm, VMAX);
+  if (s.num_hidden_layers <= 0) return fail(FQ3_ERR_INVALID, "%s: num_hidden_layers", nm);
+  return 0;
+}
+
+extern "C" int fq3_engine_create(const fq3_config* cfg, fq3_engine** out) {
+  if (!cfg || !out) return fail(FQ3_ERR_INVALID, "null argument");
+  if (cfg->dtype != FQ3_F32 && cfg->dtype != FQ3_BF16) return fail(FQ3_ERR_INVALID, "dtype must be FQ3_F32 or FQ3_BF16");
+  int rc;
+  if ((rc = check_stack(cfg->talker, "talker", 1))) return rc;
+  if ((rc = check_stack(cfg->predictor, "predictor", 2))) return rc;
+  if (cfg->talker.hidden_size > HMAX) return fail(FQ3_ERR_INVALID, "talker hidden_size > %d", HMAX);
+  if (2 * cfg->talker.hidden_size > XS_FLOATS) return fail(FQ3_ERR_INVALID, "talker hidden too large for mtp staging");
+  if (cfg->max_seq_len < 8 || cfg->max_seq_len > SEQMAX) return fail(FQ3_ERR_INVALID, "max_seq_len must be in [8,%d]", SEQMAX);
+  if (cfg->num_code_groups < 2 || cfg->num_code_groups > 16) return fail(FQ3_ERR_INVALID, "num_code_groups must be in [2,16]");
+  if (cfg->rope_positions < cfg->max_seq_len) return fail(FQ3_ERR_INVALID, "rope_positions < max_seq_len");
+  int ndev = 0;
+  CK(cudaGetDeviceCount(&ndev));
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(FQ3_ERR_INVALID, "device %d out of range", cfg->device);
+  CK(cudaSetDevice(cfg->device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, cfg->device));
+  if (prop.major < 10) return fail(FQ3_ERR_INVALID, "sm_100a required (device is sm_%d%d)", prop.major, prop.minor);
+  int coop = 0;
+  CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, cfg->device));
+  if (!coop) return fail(FQ3_ERR_INVALID, "device lacks cooperative launch");
+  fq3_engine* e = new fq3_engine();
+  e->cfg = *cfg;
+  e->bf16 = cfg->dtype == FQ3_BF16;
+  e->esz = e->bf16 ? 2 : 4;
+  e->dev = cfg->device;
+  e->ncta = cfg->num_ctas > 0 ? std::min(cfg->num_ctas, prop.multiProcessorCount) : prop.multiProcessorCount;
+  if (e->bf16) {
+    CK(cudaFuncSetAttribute(fq3_decode_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes()));
+    CK(cudaFuncSetAttribute(sample_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes()));
+  } else {
+    CK(cudaFuncSetAttribute(fq3_decode_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes()));
+    CK(cudaFuncSetAttribute(sample_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes()));
+  }
+  int occ = 0;
+  if (e->bf16) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fq3_decode_kernel<true>, NTHREADS, smem_bytes()));
+  else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fq3_decode_kernel<false>, NTHREADS, smem_bytes()));
+  if (occ < 1) { delete e; return fail(FQ3_ERR_INVALID, "decode kernel does not fit on an SM (smem %zu)", smem_bytes()); }
+
+  const fq3_stack_config &T = cfg->talker, &Pc = cfg->predictor;
+  const size_t tkv = (size_t)T.num_hidden_layers * T.num_key_value_heads * cfg->max_seq_len * 128 * e->esz;
+  const size_t pkv = (size_t)Pc.num_hidden_layers * Pc.num_key_value_heads * 32 * 128 * e->esz;
+  CK(cudaMalloc(&e->t_kc, tkv)); CK(cudaMalloc(&e->t_vc, tkv));
+  CK(cudaMalloc(&e->p_kc, pkv)); CK(cudaMalloc(&e->p_vc, pkv));
+  CK(cudaMemset(e->t_kc, 0, tkv)); CK(cudaMemset(e->t_vc, 0, tkv));
+  CK(cudaMemset(e->p_kc, 0, pkv)); CK(cudaMemset(e->p_vc, 0, pkv));
+  const int ldX = std::max(T.hidden_size, Pc.hidden_size);
+  const int ldQKV = std::max((T.num_attention_heads + 2 * T.num_key_value_heads) * 128,
+                             (Pc.num_attention_heads + 2 * Pc.num_key_value_heads) * 128);
+  const int ldATT = std::max(T.num_attention_heads, Pc.num_attention_heads) * 128;
+  const int ldACT = std::max(T.intermediate_size, Pc.intermediate_size);
+  CK(cudaMalloc(&e->X, 2 * ldX * sizeof(float))); CK(cudaMalloc(&e->X1, 2 * ldX * sizeof(float)));
+  CK(cudaMalloc(&e->QKV, 2 * ldQKV * sizeof(float))); CK(cudaMalloc(&e->ATT, 2 * ldATT * sizeof(float)));
+  CK(cudaMalloc(&e->ACT, 2 * ldACT * sizeof(float))); CK(cudaMalloc(&e->LOGITS, VMAX * sizeof(float)));
+  CK(cudaMalloc(&e->bar, 256)); CK(cudaMemset(e->bar, 0, 256));
+  CK(cudaMalloc(&e->state, 64)); CK(cudaMemset(e->state, 0, 64));
+  CK(cudaMallocHost(&e->state_host, 64));
+  CK(cudaMalloc(&e->past_hidden, HMAX * sizeof(float))); CK(cudaMemset(e->past_hidden, 0, HMAX * sizeof(float)));
+  CK(cudaMalloc(&e->seen, VMAX / 8)); CK(cudaMemset(e->seen, 0, VMAX / 8));
+  {
+    const long long rec_t = 2LL * (T.num_attention_heads + 2 * T.num_key_value_heads) * 128 + 2LL * T.num_attention_heads * 128 + 4LL * T.hidden_size + 2LL * T.intermediate_size;
+    const long long rec_p = 2LL * (Pc.num_attention_heads + 2 * Pc.num_key_value_heads) * 128 + 2LL * Pc.num_attention_heads * 128 + 4LL * Pc.hidden_size + 2LL * Pc.intermediate_size;
+    e->dbg_stride = std::max(rec_t, rec_p);
+    e->dbg_floats = (size_t)e->dbg_stride * std::max(T.num_hidden_layers, Pc.num_hidden_layers);
+    CK(cudaMalloc(&e->dbg, e->dbg_floats * sizeof(float)));
+    CK(cudaMemset(e->dbg, 0, e->dbg_floats * sizeof(float)));
+  }
+  KParams& k = e->kp;
+  memset(&k, 0, sizeof(k));
+  auto fill = [&](StackDev& s, const fq3_stack_config& c, void* kc, void* vc, int S) {
+    s.H = c.hidden_size; s.I = c.intermediate_size; s.L = c.num_hidden_layers;
+    s.nH = c.num_attention_heads; s.nKV = c.num_key_value_heads; s.V = c.vocab_size;
+    s.qd = s.nH * 128; s.kd = s.nKV * 128; s.rep = s.nH / s.nKV; s.eps = c.rms_norm_eps;
+    s.kc = kc; s.vc = vc; s.S = S;
+  };
+  fill(k.t, T, e->t_kc, e->t_vc, cfg->max_seq_len);
+  fill(k.p, Pc, e->p_kc, e->p_vc, 32);
+  k.ncta = e->ncta;
+  k.X = e->X; k.X1 = e->X1; k.QKV = e->QKV; k.ATT = e->ATT; k.ACT = e->ACT; k.LOGITS = e->LOGITS;
+  k.ldX = ldX; k.ldQKV = ldQKV; k.ldATT = ldATT; k.ldACT = ldACT;
+  k.bar = e->bar; k.state = e->state; k.past_hidden = e->past_hidden; k.seen = e->seen;
+  k.has_mtp = cfg->has_mtp_projection; k.ncb = cfg->num_code_groups - 1; k.eos = cfg->codec_eos_token_id;
+  k.max_seq_len = cfg->max_seq_len;
+  k.dbg = e->dbg; k.dbg_stride_layer = e->dbg_stride;
+  k.sp_t = Sampling{1, 50, 0.9f, 1.0f, 1.05f};
+  k.sp_p = Sampling{1, 50, 0.9f, 1.0f, 1.0f};
+  *out = e;
+  return 0;
+}
+
+extern "C" void fq3_engine_destroy(fq3_engine* e) {
+  if (!e) return;
+  cudaSetDevice(e->dev);
+  void* ptrs[] = {e->t_kc, e->t_vc, e->p_kc, e->p_vc, e->X, e->X1, e->QKV, e->ATT, e->ACT, e->LOGITS, e->bar,
+                  e->state, e->past_hidden, e->seen, e->dbg, e->tape, e->grps, e->segtab, e->cta_grp_off};
+  for (void* p : ptrs)
+    if (p) cudaFree(p);
+  for (auto& kv : e->tabs)
+    if (kv.second) cudaFree(kv.second);
+  if (e->state_host) cudaFreeHost(e->state_host);
+  delete e;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// weights: copy tables, build segments and the per-CTA tape
+// ------------------------------------------------------------------------------------------------------------
+extern "C" int fq3_engine_load_weights(fq3_engine* e, const fq3_tensor* tensors, int32_t n, void* stream_) {
+  if (!e || !tensors) return fail(FQ3_ERR_INVALID, "null argument");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  CK(cudaSetDevice(e->dev));
+  std::map<std::string, const fq3_tensor*> tm;
+  for (int i = 0; i < n; ++i) tm[tensors[i].name] = &tensors[i];
+  const fq3_config& cfg = e->cfg;
+  const size_t esz = e->esz;
+  auto need = [&](const std::string& nm, int64_t numel, const void** ptr) -> int {
+    auto it = tm.find(nm);
+    if (it == tm.end()) return fail(FQ3_ERR_INVALID, "missing tensor '%s'", nm.c_str());
+    if (it->second->numel != numel)
+      return fail(FQ3_ERR_INVALID, "tensor '%s': numel %lld, expected %lld", nm.c_str(), (long long)it->second->numel, (long long)numel);
+    *ptr = it->second->dev_ptr;
+    return 0;
+  };
+  int rc;
+  // ---- small tables: copied into engine-owned storage
+  auto own = [&](const std::string& nm, int64_t numel, size_t elem, const void** devp) -> int {
+    const void* src;
+    if ((rc = need(nm, numel, &src))) return rc;
+    void* dst = nullptr;
+    auto it = e->tabs.find(nm);
+    if (it != e->tabs.end() && it->second) cudaFree(it->second);
+    CK(cudaMalloc(&dst, (size_t)numel * elem));
+    CK(cudaMemcpyAsync(dst, src, (size_t)numel * elem, cudaMemcpyDeviceToDevice, stream));
+    e->tabs[nm] = dst;
+    *devp = dst;
+    return 0;
+  };
+  KParams& k = e->kp;
+  struct StackNames { const char* pre; StackDev* s; const fq3_stack_config* c; };
+  StackNames sn[2] = {{"t.", &k.t, &cfg.talker}, {"p.", &k.p, &cfg.predictor}};
+  for (auto& s : sn) {
+    const std::string p = s.pre;
+    const int L = s.c->num_hidden_layers, H = s.c->hidden_size;
+    if ((rc = own(p + "ln_in", (int64_t)L * H, esz, &s.s->ln_in))) return rc;
+    if ((rc = own(p + "ln_post", (int64_t)L * H, esz, &s.s->ln_post))) return rc;
+    if ((rc = own(p + "qnorm", (int64_t)L * 128, esz, &s.s->qnorm))) return rc;
+    if ((rc = own(p + "knorm", (int64_t)L * 128, esz, &s.s->knorm))) return rc;
+    if ((rc = own(p + "ln_f", H, esz, &s.s->ln_f))) return rc;
+  }
+  {
+    const void* p;
+    if ((rc = own("t.cos", (int64_t)cfg.rope_positions * 128, 4, &p))) return rc; k.t.cos = (const float*)p;
+    if ((rc = own("t.sin", (int64_t)cfg.rope_positions * 128, 4, &p))) return rc; k.t.sin = (const float*)p;
+    k.t.npos = cfg.rope_positions;
+    if ((rc = own("p.cos", 32 * 128, 4, &p))) return rc; k.p.cos = (const float*)p;
+    if ((rc = own("p.sin", 32 * 128, 4, &p))) return rc; k.p.sin = (const float*)p;
+    k.p.npos = 32;
+    const int Ht = cfg.talker.hidden_size;
+    if ((rc = own("t.embed", (int64_t)cfg.talker.vocab_size * Ht, esz, &k.t_embed))) return rc;
+    if ((rc = own("p.embeds", (int64_t)k.ncb * cfg.predictor.vocab_size * Ht, esz, &k.p_embeds))) return rc;
+    if (cfg.has_mtp_projection) {
+      if ((rc = own("p.mtp_b", cfg.predictor.hidden_size, esz, &k.mtp_b))) return rc;
+    } else {
+      k.mtp_b = nullptr;
+    }
+  }
+  // ---- segments and their row sources
+  std::vector<SegHost>& segs = e->segs;
+  segs.clear();
+  std::vector<const void*> rowsrc;          // concatenated row pointers
+  std::vector<uint32_t> seg_rowsrc0;        // first index into rowsrc per segment
+  auto add_seg = [&](int rows, int K) {
+    segs.push_back(SegHost{rows, K, 0});
+    seg_rowsrc0.push_back((uint32_t)rowsrc.size());
+  };
+  auto push_rows = [&](const void* base, int64_t row0, int rows, int K, int stride_rows = 1, int start = 0) {
+    (void)stride_rows; (void)start;
+    for (int r = 0; r < rows; ++r) rowsrc.push_back((const uint8_t*)base + (size_t)(row0 + r) * K * esz);
+  };
+  int seg_id = 0;
+  for (int si = 0; si < 2; ++si) {
+    const std::string p = sn[si].pre;
+    const fq3_stack_config& c = *sn[si].c;
+    const int L = c.num_hidden_layers, H = c.hidden_size, I = c.intermediate_size;
+    const int qd = c.num_attention_heads * 128, kd = c.num_key_value_heads * 128;
+    const void *wq, *wk, *wv, *wo, *wg, *wu, *wd;
+    if ((rc = need(p + "q", (int64_t)L * qd * H, &wq))) return rc;
+    if ((rc = need(p + "k", (int64_t)L * kd * H, &wk))) return rc;
+    if ((rc = need(p + "v", (int64_t)L * kd * H, &wv))) return rc;
+    if ((rc = need(p + "o", (int64_t)L * H * qd, &wo))) return rc;
+    if ((rc = need(p + "gate", (int64_t)L * I * H, &wg))) return rc;
+    if ((rc = need(p + "up", (int64_t)L * I * H, &wu))) return rc;
+    if ((rc = need(p + "down", (int64_t)L * H * I, &wd))) return rc;
+    sn[si].s->seg_base = seg_id;
+    for (int l = 0; l < L; ++l) {
+      add_seg(qd + 2 * kd, H);
+      push_rows(wq, (int64_t)l * qd, qd, H);
+      push_rows(wk, (int64_t)l * kd, kd, H);
+      push_rows(wv, (int64_t)l * kd, kd, H);
+      add_seg(H, qd);
+      push_rows(wo, (int64_t)l * H, H, qd);
+      add_seg(2 * I, H);
+      for (int r = 0; r < I; ++r) {
+        rowsrc.push_back((const uint8_t*)wg + ((size_t)l * I + r) * H * esz);
+        rowsrc.push_back((const uint8_t*)wu + ((size_t)l * I + r) * H * esz);
+      }
+      add_seg(H, I);
+      push_rows(wd, (int64_t)l * H, H, I);
+      seg_id += 4;
+    }
+    if (si == 0) {
+      const void* wh;
+      if ((rc = need("t.head", (int64_t)c.vocab_size * H, &wh))) return rc;
+      sn[si].s->seg_head = seg_id;
+      add_seg(c.vocab_size, H);
+      push_rows(wh, 0, c.vocab_size, H);
+      seg_id += 1;
+    } else {
+      const void* wh;
+      if ((rc = need("p.heads", (int64_t)k.ncb * c.vocab_size * H, &wh))) return rc;
+      sn[si].s->seg_head = seg_id;
+      for (int i = 0; i < k.ncb; ++i) {
+        add_seg(c.vocab_size, H);
+        push_rows(wh, (int64_t)i * c.vocab_size, c.vocab_size, H);
+        seg_id += 1;
+      }
+      if (cfg.has_mtp_projection) {
+        const void* wm;
+        const int Ht = cfg.talker.hidden_size;
+        if ((rc = need("p.mtp_w", (int64_t)H * Ht, &wm))) return rc;
+        k.seg_mtp = seg_id;
+        add_seg(H, Ht);
+        push_rows(wm, 0, H, Ht);
+        seg_id += 1;
+      } else {
+        k.seg_mtp = -1;
+      }
+    }
+  }
+  const int nseg = (int)segs.size();
+  if (nseg > MAXSEG) return fail(FQ3_ERR_INVALID, "too many segments (%d > %d)", nseg, MAXSEG);
+  k.nseg = nseg;
+  // ---- distribute row pairs over CTAs, split into groups, lay out the tape
+  const int ncta = e->ncta;
+  const int EPW = e->bf16 ? 256 : 128;  // elements per 512-byte warp read
+  std::vector<std::vector<Grp>> cta_grps(ncta);
+  std::vector<uint32_t> segtab((size_t)ncta * nseg, 0);
+  std::vector<PackGrp> pack;
+  // per-CTA byte totals to place groups: first pass collects sizes
+  struct Tmp { int cta, seg, row0, rows, m, ntiles; uint64_t bytes; };
+  std::vector<Tmp> tmp;
+  int rot = 0;
+  for (int sg = 0; sg < nseg; ++sg) {
+    const int rows = segs[sg].rows, K = segs[sg].K;
+    if (rows % 2 || K % EPW) return fail(FQ3_ERR_INVALID, "segment %d: rows %d must be even and K %d a multiple of %d", sg, rows, K, EPW);
+    const int KB = K / EPW;
+    const int pairs = rows / 2, base = pairs / ncta, extra = pairs % ncta;
+    int row = 0;
+    for (int c = 0; c < ncta; ++c) {
+      const int pc = base + ((((c - rot) % ncta + ncta) % ncta) < extra ? 1 : 0);
+      const int rows_c = 2 * pc;
+      const int ng = (rows_c + 31) / 32;
+      int begin = (int)cta_grps[c].size();
+      int r0 = row;
+      for (int gi = 0; gi < ng; ++gi) {
+        const int gp = pc / ng + (gi < pc % ng ? 1 : 0);
+        const int gr = 2 * gp;
+        int m = 1;
+        for (int d = 1; d <= KB; ++d)
+          if (KB % d == 0 && (size_t)gr * 512 * d <= (size_t)STAGE_BYTES) m = d;
+        const int ntiles = KB / m;
+        Tmp t{c, sg, r0, gr, m, ntiles, (uint64_t)gr * K * esz};
+        tmp.push_back(t);
+        Grp g; g.off16 = 0; g.row0 = r0; g.rows = (uint16_t)gr; g.m = (uint16_t)m; g.ntiles = (uint16_t)ntiles; g.pad = 0;
+        cta_grps[c].push_back(g);
+        r0 += gr;
+      }
+      if (ng > 255) return fail(FQ3_ERR_INVALID, "segment %d: too many groups per CTA", sg);
+      segtab[(size_t)c * nseg + sg] = ((uint32_t)begin << 8) | (uint32_t)ng;
+      row += rows_c;
+    }
+    rot = (rot + extra) % ncta;
+    segs[sg].bytes = (uint64_t)rows * K * esz;
+  }
+  // tape offsets: CTA-major, segment order
+  std::vector<uint64_t> cta_base(ncta + 1, 0);
+  {
+    std::vector<uint64_t> sz(ncta, 0);
+    for (auto& t : tmp) sz[t.cta] += t.bytes;
+    for (int c = 0; c < ncta; ++c) cta_base[c + 1] = cta_base[c] + ((sz[c] + 1023) / 1024) * 1024;
+  }
+  const uint64_t tape_bytes = cta_base[ncta];
+  if (tape_bytes / 16 > 0xffffffffull) return fail(FQ3_ERR_INVALID, "tape too large");
+  {
+    std::vector<uint64_t> cur(cta_base.begin(), cta_base.end() - 1);
+    std::vector<int> gidx(ncta, 0);
+    for (auto& t : tmp) {
+      Grp& g = cta_grps[t.cta][gidx[t.cta]++];
+      g.off16 = (uint32_t)(cur[t.cta] / 16);
+      PackGrp pg; pg.tape_off = cur[t.cta]; pg.rowsrc_idx = seg_rowsrc0[t.seg] + (uint32_t)t.row0;
+      pg.rows = (uint16_t)t.rows; pg.m = (uint16_t)t.m; pg.ntiles = (uint16_t)t.ntiles; pg.pad = 0; pg.K = segs[t.seg].K;
+      pack.push_back(pg);
+      cur[t.cta] += t.bytes;
+    }
+  }
+  std::vector<uint32_t> goff(ncta + 1, 0);
+  std::vector<Grp> allg;
+  for (int c = 0; c < ncta; ++c) {
+    if ((int)cta_grps[c].size() > MAXGRP) return fail(FQ3_ERR_INVALID, "CTA %d has %zu row groups (> %d)", c, cta_grps[c].size(), MAXGRP);
+    goff[c + 1] = goff[c] + (uint32_t)cta_grps[c].size();
+    allg.insert(allg.end(), cta_grps[c].begin(), cta_grps[c].end());
+  }
+  // ---- upload tables, pack
+  if (e->tape) { cudaFree(e->tape); e->tape = nullptr; }
+  if (e->grps) { cudaFree(e->grps); e->grps = nullptr; }
+  if (e->segtab) { cudaFree(e->segtab); e->segtab = nullptr; }
+  if (e->cta_grp_off) { cudaFree(e->cta_grp_off); e->cta_grp_off = nullptr; }
+  CK(cudaMalloc(&e->tape, tape_bytes));
+  e->tape_bytes = tape_bytes;
+  CK(cudaMalloc(&e->grps, allg.size() * sizeof(Grp)));
+  CK(cudaMalloc(&e->segtab, segtab.size() * sizeof(uint32_t)));
+  CK(cudaMalloc(&e->cta_grp_off, goff.size() * sizeof(uint32_t)));
+  CK(cudaMemcpyAsync(e->grps, allg.data(), allg.size() * sizeof(Grp), cudaMemcpyHostToDevice, stream));
+  CK(cudaMemcpyAsync(e->segtab, segtab.data(), segtab.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
+  CK(cudaMemcpyAsync(e->cta_grp_off, goff.data(), goff.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
+  void** d_rowsrc = nullptr;
+  PackGrp* d_pack = nullptr;
+  CK(cudaMalloc(&d_rowsrc, rowsrc.size() * sizeof(void*)));
+  CK(cudaMalloc(&d_pack, pack.size() * sizeof(PackGrp)));
+  CK(cudaMemcpyAsync(d_rowsrc, rowsrc.data(), rowsrc.size() * sizeof(void*), cudaMemcpyHostToDevice, stream));
+  CK(cudaMemcpyAsync(d_pack, pack.data(), pack.size() * sizeof(PackGrp), cudaMemcpyHostToDevice, stream));
+  {
+    const int grid = (int)std::min<size_t>(pack.size(), 148 * 16);
+    if (e->bf16) pack_kernel<true><<<grid, 256, 0, stream>>>(d_pack, (int)pack.size(), (const void* const*)d_rowsrc, e->tape);
+    else pack_kernel<false><<<grid, 256, 0, stream>>>(d_pack, (int)pack.size(), (const void* const*)d_rowsrc, e->tape);
+    e->launches++;
+    CK(cudaGetLastError());
+  }
+  CK(cudaStreamSynchronize(stream));
+  cudaFree(d_rowsrc);
+  cudaFree(d_pack);
+  k.tape = e->tape; k.grps = e->grps; k.segtab = e->segtab; k.cta_grp_off = e->cta_grp_off;
+  // ---- byte accounting (algorithmic bytes)
+  {
+    uint64_t tl = 0, pl = 0, ph = 0, pm = 0;
+    for (int l = 0; l < k.t.L * 4; ++l) tl += segs[k.t.seg_base + l].bytes;
+    tl += segs[k.t.seg_head].bytes;
+    for (int l = 0; l < k.p.L * 4; ++l) pl += segs[k.p.seg_base + l].bytes;
+    for (int i = 0; i < k.ncb; ++i) ph += segs[k.p.seg_head + i].bytes;
+    if (k.seg_mtp >= 0) pm = segs[k.seg_mtp].bytes;
+    e->talker_step_bytes = (int64_t)tl;
+    e->predictor_frame_bytes = (int64_t)(k.ncb * (pl + pm) + ph);
+  }
+  e->loaded = true;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// launches
+// ------------------------------------------------------------------------------------------------------------
+static int launch_decode(fq3_engine* e, const KParams& kp, cudaStream_t stream) {
+  CK(cudaMemsetAsync(e->bar, 0, 4, stream));
+  void* args[] = {(void*)&kp};
+  if (e->bf16)
+    CK(cudaLaunchCooperativeKernel((const void*)fq3_decode_kernel<true>, dim3(e->ncta), dim3(NTHREADS), args, smem_bytes(), stream));
+  else
+    CK(cudaLaunchCooperativeKernel((const void*)fq3_decode_kernel<false>, dim3(e->ncta), dim3(NTHREADS), args, smem_bytes(), stream));
+  e->launches++;
+  return 0;
+}
+
+static Sampling to_sampling(const fq3_sampling* s) {
+  Sampling r;
+  r.do_sample = s->do_sample; r.top_k = s->top_k; r.temperature = s->temperature; r.top_p = s->top_p;
+  r.penalty = s->repetition_penalty;
+  return r;
+}
+
+extern "C" int fq3_import_kv(fq3_engine* e, int32_t layer, const void* k_dev, const void* v_dev, int32_t P, void* stream_) {
+  if (!e || !k_dev || !v_dev) return fail(FQ3_ERR_INVALID, "null argument");
+  if (P > e->cfg.max_seq_len)
+    return fail(FQ3_ERR_TOO_LONG, "Input is too long: prefill has %d tokens but max_seq_len=%d. Use shorter text or shorter reference audio.", P, e->cfg.max_seq_len);
+  if (layer < 0 || layer >= e->cfg.talker.num_hidden_layers) return fail(FQ3_ERR_INVALID, "layer out of range");
+  CK(cudaSetDevice(e->dev));
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const int nKV = e->cfg.talker.num_key_value_heads, S = e->cfg.max_seq_len;
+  const size_t row = (size_t)P * 128 * e->esz, pitch = (size_t)S * 128 * e->esz;
+  uint8_t* kd = (uint8_t*)e->t_kc + (size_t)layer * nKV * pitch;
+  uint8_t* vd = (uint8_t*)e->t_vc + (size_t)layer * nKV * pitch;
+  if (P > 0) {
+    CK(cudaMemcpy2DAsync(kd, pitch, k_dev, row, row, nKV, cudaMemcpyDeviceToDevice, stream));
+    CK(cudaMemcpy2DAsync(vd, pitch, v_dev, row, row, nKV, cudaMemcpyDeviceToDevice, stream));
+  }
+  return 0;
+}
+
+extern "C" int fq3_set_generation_state(fq3_engine* e, int32_t n_left_pad, int32_t rope_delta) {
+  if (!e) return fail(FQ3_ERR_INVALID, "null argument");
+  e->kp.n_left_pad = n_left_pad;
+  e->kp.rope_delta = rope_delta;
+  return 0;
+}
+
+extern "C" int fq3_talker_step(fq3_engine* e, const void* embeds_dev, int32_t position, void* hidden_out_dev, void* stream_) {
+  if (!e || !embeds_dev || !hidden_out_dev) return fail(FQ3_ERR_INVALID, "null argument");
+  if (!e->loaded) return fail(FQ3_ERR_STATE, "weights not loaded");
+  if (position < 0 || position >= e->cfg.max_seq_len) return fail(FQ3_ERR_INVALID, "position %d outside the cache", position);
+  CK(cudaSetDevice(e->dev));
+  KParams kp = e->kp;
+  kp.mode = MODE_TALKER_STEP;
+  kp.in_embeds = embeds_dev; kp.hidden_out = hidden_out_dev; kp.position = position;
+  kp.dbg_on = e->dbg_on;
+  return launch_decode(e, kp, (cudaStream_t)stream_);
+}
+
+extern "C" int fq3_predictor_run(fq3_engine* e, const void* pred_input_dev, const fq3_sampling* sp, const float* uniforms_dev,
+                                 int64_t* codes_out_dev, void* stream_) {
+  if (!e || !pred_input_dev || !sp || !codes_out_dev) return fail(FQ3_ERR_INVALID, "null argument");
+  if (!e->loaded) return fail(FQ3_ERR_STATE, "weights not loaded");
+  if (sp->do_sample && !uniforms_dev) return fail(FQ3_ERR_INVALID, "do_sample needs uniforms");
+  CK(cudaSetDevice(e->dev));
+  KParams kp = e->kp;
+  kp.mode = MODE_PRED_RUN;
+  kp.pred_input = pred_input_dev; kp.pred_uniforms = uniforms_dev; kp.codes_out = (long long*)codes_out_dev;
+  kp.sp_p = to_sampling(sp);
+  kp.dbg_on = e->dbg_on;
+  return launch_decode(e, kp, (cudaStream_t)stream_);
+}
+
+extern "C" int fq3_sample_logits(fq3_engine* e, const void* logits_dev, int32_t V, const fq3_sampling* sp, float u,
+                                 const int64_t* history_dev, int32_t n_hist, int32_t suppress_special, int32_t eos_id,
+                                 int32_t suppress_eos, int64_t* token_out_dev, void* stream_) {
+  if (!e || !logits_dev || !sp || !token_out_dev) return fail(FQ3_ERR_INVALID, "null argument");
+  if (V <= 0 || V > VMAX) return fail(FQ3_ERR_INVALID, "V out of range");
+  CK(cudaSetDevice(e->dev));
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const Sampling s = to_sampling(sp);
+  if (e->bf16)
+    sample_kernel<true><<<1, NCT, smem_bytes(), stream>>>(e->kp, logits_dev, V, s, u, (const long long*)history_dev, history_dev ? n_hist : 0, suppress_special, eos_id, suppress_eos, (long long*)token_out_dev);
+  else
+    sample_kernel<false><<<1, NCT, smem_bytes(), stream>>>(e->kp, logits_dev, V, s, u, (const long long*)history_dev, history_dev ? n_hist : 0, suppress_special, eos_id, suppress_eos, (long long*)token_out_dev);
+  e->launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int fq3_begin_request(fq3_engine* e, const fq3_request* rq, const void* past_hidden_dev, const void* trailing_text_dev,
+                                 const void* tts_pad_dev, const float* uniforms_dev, const fq3_sampling* sp_talker,
+                                 const fq3_sampling* sp_predictor, void* stream_) {
+  if (!e || !rq || !past_hidden_dev || !tts_pad_dev || !sp_talker || !sp_predictor) return fail(FQ3_ERR_INVALID, "null argument");
+  if (!e->loaded) return fail(FQ3_ERR_STATE, "weights not loaded");
+  if (rq->prefill_len > e->cfg.max_seq_len)
+    return fail(FQ3_ERR_TOO_LONG, "Input is too long: prefill has %d tokens but max_seq_len=%d. Use shorter text or shorter reference audio.", rq->prefill_len, e->cfg.max_seq_len);
+  if ((sp_talker->do_sample || sp_predictor->do_sample) && !uniforms_dev) return fail(FQ3_ERR_INVALID, "sampling needs uniforms");
+  if (rq->trailing_len > 0 && !trailing_text_dev) return fail(FQ3_ERR_INVALID, "trailing_len > 0 but no trailing text");
+  if (rq->first_token < 0 || rq->first_token >= e->cfg.talker.vocab_size) return fail(FQ3_ERR_INVALID, "first_token out of range");
+  CK(cudaSetDevice(e->dev));
+  cudaStream_t stream = (cudaStream_t)stream_;
+  KParams& k = e->kp;
+  k.prefill_len = rq->prefill_len; k.rope_delta = rq->rope_delta; k.n_left_pad = rq->n_left_pad;
+  k.max_new = rq->max_new_tokens; k.min_new = rq->min_new_tokens; k.trailing_len = rq->trailing_len;
+  k.trailing = trailing_text_dev; k.tts_pad = tts_pad_dev; k.uniforms = uniforms_dev;
+  k.sp_t = to_sampling(sp_talker); k.sp_p = to_sampling(sp_predictor);
+  if (e->bf16) set_state_kernel<true><<<4, 256, 0, stream>>>(e->state, e->past_hidden, e->seen, past_hidden_dev, e->cfg.talker.hidden_size, rq->first_token, rq->gen_step);
+  else set_state_kernel<false><<<4, 256, 0, stream>>>(e->state, e->past_hidden, e->seen, past_hidden_dev, e->cfg.talker.hidden_size, rq->first_token, rq->gen_step);
+  e->launches++;
+  CK(cudaGetLastError());
+  e->request_active = true;
+  return 0;
+}
+
+extern "C" int fq3_decode_chunk(fq3_engine* e, int32_t n_frames, int64_t* codes_out_dev, fq3_chunk_result* res, void* stream_) {
+  if (!e || !codes_out_dev || !res) return fail(FQ3_ERR_INVALID, "null argument");
+  if (!e->request_active) return fail(FQ3_ERR_STATE, "fq3_begin_request has not been called");
+  if (n_frames <= 0) return fail(FQ3_ERR_INVALID, "n_frames must be positive");
+  CK(cudaSetDevice(e->dev));
+  cudaStream_t stream = (cudaStream_t)stream_;
+  KParams kp = e->kp;
+  kp.mode = MODE_FUSED;
+  kp.n_frames = n_frames;
+  kp.codes_out = (long long*)codes_out_dev;
+  kp.dbg_on = 0;
+  int rc = launch_decode(e, kp, stream);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(e->state_host, e->state, 32, cudaMemcpyDeviceToHost, stream));
+  CK(cudaStreamSynchronize(stream));
+  res->next_token = e->state_host[0];
+  res->total_frames = e->state_host[1];
+  res->finished = e->state_host[3];
+  res->frames_emitted = e->state_host[4];
+  return 0;
+}
+
+extern "C" int fq3_get_past_hidden(fq3_engine* e, void* dst_dev, void* stream_) {
+  if (!e || !dst_dev) return fail(FQ3_ERR_INVALID, "null argument");
+  CK(cudaSetDevice(e->dev));
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (e->bf16) get_hidden_kernel<true><<<4, 256, 0, stream>>>(e->past_hidden, dst_dev, e->cfg.talker.hidden_size);
+  else get_hidden_kernel<false><<<4, 256, 0, stream>>>(e->past_hidden, dst_dev, e->cfg.talker.hidden_size);
+  e->launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int fq3_debug_enable(fq3_engine* e, int32_t on) {
+  if (!e) return fail(FQ3_ERR_INVALID, "null argument");
+  e->dbg_on = on ? 1 : 0;
+  return 0;
+}
+
+extern "C" int fq3_debug_read(fq3_engine* e, int64_t offset, int64_t count, float* host_dst) {
+  if (!e || !host_dst) return fail(FQ3_ERR_INVALID, "null argument");
+  if (offset < 0 || count < 0 || (size_t)(offset + count) > e->dbg_floats) return fail(FQ3_ERR_INVALID, "debug range outside the buffer (%zu floats)", e->dbg_floats);
+  CK(cudaSetDevice(e->dev));
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy(host_dst, e->dbg + offset, (size_t)count * sizeof(float), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+extern "C" int fq3_tape_bytes(fq3_engine* e, int64_t* talker_step_bytes, int64_t* predictor_frame_bytes) {
+  if (!e) return fail(FQ3_ERR_INVALID, "null argument");
+  if (talker_step_bytes) *talker_step_bytes = e->talker_step_bytes;
+  if (predictor_frame_bytes) *predictor_frame_bytes = e->predictor_frame_bytes;
+  return 0;
+}
+
+extern "C" int fq3_num_ctas(fq3_engine* e) { return e ? e->ncta : 0; }
+extern "C" int64_t fq3_launch_count(fq3_engine* e) { return e ? e->launches : 0; }
+extern "C" const char* fq3_last_error(void) { return g_err; }
+extern "C" const char* fq3_version(void) { return "fq3-b200 0.1.0 (sm_100a)"; }
