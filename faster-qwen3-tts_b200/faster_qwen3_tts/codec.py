@@ -1,0 +1,251 @@
+"""Codec decoder (RVQ codes -> 24 kHz PCM) behind the ``speech_tokenizer.decode`` contract the reference calls
+(model.py:924,1093,1122; tests/test_sample_rate.py:53-75):
+
+    speech_tokenizer.decode({"audio_codes": LongTensor[1, T, 16]}) -> ([wav Tensor[1920*T]], 24000)
+
+The real Qwen3-TTS tokenizer decoder ships inside the absent ``qwen-tts`` package; its geometry is restated from the
+in-image analogue ``transformers/models/qwen3_omni_moe/modeling_qwen3_omni_moe.py`` (Code2Wav :3730-3790, causal
+convs :3283-3330, ConvNeXt :3333-3366, SnakeBeta :3645-3683, decoder block :3705-3727, pre-transformer :3370-3640):
+16-codebook embedding mean -> 8-layer sliding-window pre-transformer (H=1024) -> 2x(ConvTranspose k=2,s=2 + ConvNeXt)
+-> conv7 1024->1536 -> 4 blocks [SnakeBeta, causal ConvTranspose (k=2r, s=r), 3 residual units (SnakeBeta, dilated
+conv7, SnakeBeta, conv1)] with r = 8,5,4,3 and channels 1536->768->384->192->96 -> SnakeBeta -> conv7 -> clamp.
+Total upsample 1920.  "parity unpinned" (analogue geometry, synthetic weights).
+
+Round 1: the module below is the torch-library implementation (cuDNN / cuBLAS), used as the functional baseline
+and as the weight container; the sm_100a kernels replace its hot layers through the C ABI as they land
+(kernel K4).
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import List, Tuple
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+
+@dataclass
+class Code2WavConfig:
+    codebook_size: int = 2048
+    num_quantizers: int = 16
+    hidden_size: int = 1024
+    num_hidden_layers: int = 8
+    num_attention_heads: int = 16
+    intermediate_size: int = 3072
+    sliding_window: int = 72
+    rms_norm_eps: float = 1e-5
+    layer_scale: float = 0.01
+    rope_theta: float = 10000.0
+    upsampling_ratios: Tuple[int, ...] = (2, 2)
+    upsample_rates: Tuple[int, ...] = (8, 5, 4, 3)
+    decoder_dim: int = 1536
+    sample_rate: int = 24000
+
+    @property
+    def total_upsample(self) -> int:
+        return int(math.prod(self.upsampling_ratios) * math.prod(self.upsample_rates))
+
+
+def tiny_codec_config() -> Code2WavConfig:
+    return Code2WavConfig(codebook_size=64, hidden_size=128, num_hidden_layers=2, num_attention_heads=2,
+                          intermediate_size=256, sliding_window=8, decoder_dim=64)
+
+
+class CausalConv1d(nn.Module):
+    def __init__(self, cin, cout, k, dilation=1, groups=1):
+        super().__init__()
+        self.conv = nn.Conv1d(cin, cout, k, dilation=dilation, groups=groups)
+        self.pad = (k - 1) * dilation
+
+    def forward(self, x):
+        return self.conv(F.pad(x, (self.pad, 0)))
+
+
+class CausalConvTranspose1d(nn.Module):
+    def __init__(self, cin, cout, k, stride):
+        super().__init__()
+        self.conv = nn.ConvTranspose1d(cin, cout, k, stride=stride)
+        self.trim = k - stride
+
+    def forward(self, x):
+        y = self.conv(x)  # length (T-1)*s + k; dropping the k-s tail keeps it causal and exactly T*s long
+        return y[..., : y.shape[-1] - self.trim] if self.trim else y
+
+
+class SnakeBeta(nn.Module):
+    def __init__(self, c):
+        super().__init__()
+        self.alpha = nn.Parameter(torch.zeros(c))
+        self.beta = nn.Parameter(torch.zeros(c))
+
+    def forward(self, x):
+        a = torch.exp(self.alpha)[None, :, None]
+        b = torch.exp(self.beta)[None, :, None]
+        return x + (1.0 / (b + 1e-9)) * torch.sin(x * a).pow(2)
+
+
+class ConvNeXt(nn.Module):
+    def __init__(self, c):
+        super().__init__()
+        self.dwconv = CausalConv1d(c, c, 7, groups=c)
+        self.norm = nn.LayerNorm(c, eps=1e-6)
+        self.pwconv1 = nn.Linear(c, 4 * c)
+        self.pwconv2 = nn.Linear(4 * c, c)
+        self.gamma = nn.Parameter(1e-6 * torch.ones(c))
+
+    def forward(self, x):
+        h = self.dwconv(x).transpose(1, 2)
+        h = self.pwconv2(F.gelu(self.pwconv1(self.norm(h))))
+        return x + (self.gamma * h).transpose(1, 2)
+
+
+class ResidualUnit(nn.Module):
+    def __init__(self, c, dilation):
+        super().__init__()
+        self.act1, self.conv1 = SnakeBeta(c), CausalConv1d(c, c, 7, dilation=dilation)
+        self.act2, self.conv2 = SnakeBeta(c), CausalConv1d(c, c, 1)
+
+    def forward(self, x):
+        return x + self.conv2(self.act2(self.conv1(self.act1(x))))
+
+
+class DecoderBlock(nn.Module):
+    def __init__(self, cin, cout, rate):
+        super().__init__()
+        self.act = SnakeBeta(cin)
+        self.up = CausalConvTranspose1d(cin, cout, 2 * rate, rate)
+        self.res = nn.ModuleList([ResidualUnit(cout, d) for d in (1, 3, 9)])
+
+    def forward(self, x):
+        x = self.up(self.act(x))
+        for r in self.res:
+            x = r(x)
+        return x
+
+
+class _RMS(nn.Module):
+    def __init__(self, n, eps):
+        super().__init__()
+        self.weight = nn.Parameter(torch.ones(n))
+        self.eps = eps
+
+    def forward(self, x):
+        dt = x.dtype
+        xf = x.float()
+        return self.weight * (xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + self.eps)).to(dt)
+
+
+class PreLayer(nn.Module):
+    def __init__(self, c: Code2WavConfig):
+        super().__init__()
+        H, I = c.hidden_size, c.intermediate_size
+        self.nh = c.num_attention_heads
+        self.q, self.k, self.v, self.o = (nn.Linear(H, H, bias=False) for _ in range(4))
+        self.gate, self.up, self.down = nn.Linear(H, I, bias=False), nn.Linear(H, I, bias=False), nn.Linear(I, H, bias=False)
+        self.ln1, self.ln2 = _RMS(H, c.rms_norm_eps), _RMS(H, c.rms_norm_eps)
+        self.s1 = nn.Parameter(torch.full((H,), c.layer_scale))
+        self.s2 = nn.Parameter(torch.full((H,), c.layer_scale))
+
+    def forward(self, x, cos, sin, mask):
+        B, T, H = x.shape
+        hd = H // self.nh
+        h = self.ln1(x)
+        q = self.q(h).view(B, T, self.nh, hd).transpose(1, 2)
+        k = self.k(h).view(B, T, self.nh, hd).transpose(1, 2)
+        v = self.v(h).view(B, T, self.nh, hd).transpose(1, 2)
+
+        def rot(t):
+            a, b = t[..., : hd // 2], t[..., hd // 2:]
+            return torch.cat((-b, a), dim=-1)
+
+        q = q * cos + rot(q) * sin
+        k = k * cos + rot(k) * sin
+        o = F.scaled_dot_product_attention(q, k, v, attn_mask=mask)
+        x = x + self.s1 * self.o(o.transpose(1, 2).reshape(B, T, H))
+        h = self.ln2(x)
+        return x + self.s2 * self.down(F.silu(self.gate(h)) * self.up(h))
+
+
+class Code2Wav(nn.Module):
+    def __init__(self, c: Code2WavConfig):
+        super().__init__()
+        self.config = c
+        H = c.hidden_size
+        self.code_embedding = nn.Embedding(c.codebook_size * c.num_quantizers, H)
+        self.layers = nn.ModuleList([PreLayer(c) for _ in range(c.num_hidden_layers)])
+        self.norm = _RMS(H, c.rms_norm_eps)
+        self.upsample = nn.ModuleList([nn.ModuleList([CausalConvTranspose1d(H, H, r, r), ConvNeXt(H)])
+                                       for r in c.upsampling_ratios])
+        self.conv_in = CausalConv1d(H, c.decoder_dim, 7)
+        chans = [c.decoder_dim // (2 ** i) for i in range(len(c.upsample_rates) + 1)]
+        self.blocks = nn.ModuleList([DecoderBlock(chans[i], chans[i + 1], r) for i, r in enumerate(c.upsample_rates)])
+        self.act_out = SnakeBeta(chans[-1])
+        self.conv_out = CausalConv1d(chans[-1], 1, 7)
+
+    def forward(self, codes: torch.Tensor) -> torch.Tensor:
+        """codes [B, Q, T] -> wav [B, 1, 1920*T] clamped to [-1, 1]."""
+        c = self.config
+        B, Q, T = codes.shape
+        off = (torch.arange(Q, device=codes.device) * c.codebook_size).view(1, Q, 1)
+        x = self.code_embedding(codes + off).mean(1)  # [B,T,H]
+        hd = c.hidden_size // c.num_attention_heads
+        inv = 1.0 / (c.rope_theta ** (torch.arange(0, hd, 2, dtype=torch.float32, device=x.device) / hd))
+        fr = torch.arange(T, dtype=torch.float32, device=x.device)[:, None] * inv[None]
+        emb = torch.cat((fr, fr), dim=-1)
+        cos, sin = emb.cos().to(x.dtype)[None, None], emb.sin().to(x.dtype)[None, None]
+        i = torch.arange(T, device=x.device)
+        allowed = (i[None, :] <= i[:, None]) & (i[None, :] > i[:, None] - c.sliding_window)
+        for l in self.layers:
+            x = l(x, cos, sin, allowed)
+        x = self.norm(x).transpose(1, 2)
+        for up, nx in self.upsample:
+            x = nx(up(x))
+        x = self.conv_in(x)
+        for b in self.blocks:
+            x = b(x)
+        return self.conv_out(self.act_out(x)).clamp(-1, 1)
+
+
+class SpeechTokenizer:
+    """The decode side of the upstream speech tokenizer, as the reference consumes it."""
+
+    def __init__(self, decoder: Code2Wav):
+        self.decoder = decoder
+        self.sample_rate = decoder.config.sample_rate
+        self.launches = 0
+
+    @torch.inference_mode()
+    def decode(self, payload) -> Tuple[List[torch.Tensor], int]:
+        codes = payload["audio_codes"]  # [B, T, Q]
+        dev = next(self.decoder.parameters()).device
+        wav = self.decoder(codes.to(dev).transpose(1, 2))
+        self.launches += 1
+        return [w.reshape(-1).float() for w in wav], self.sample_rate
+
+
+def build_codec(cfg: Code2WavConfig = None, seed: int = 0, dtype=torch.bfloat16, device="cpu") -> SpeechTokenizer:
+    cfg = cfg or Code2WavConfig()
+    dev = torch.device(device)
+    with torch.device(dev):
+        m = Code2Wav(cfg)
+    g = torch.Generator(device=dev).manual_seed(seed)
+    for name, p in m.named_parameters():
+        p.requires_grad_(False)
+        if name.endswith(("alpha", "beta")):
+            p.normal_(0.0, 0.3, generator=g)
+        elif name.endswith("gamma"):
+            p.fill_(0.1)
+        elif ".s1" in name or ".s2" in name:
+            pass
+        elif p.dim() == 1 and ("ln" in name or "norm" in name) and name.endswith("weight"):
+            p.fill_(1.0)
+        elif p.dim() == 1:
+            p.normal_(0.0, 0.01, generator=g)
+        elif "code_embedding" in name:
+            p.normal_(0.0, 1.0, generator=g)
+        else:
+            fan_in = p[0].numel()
+            p.normal_(0.0, 1.0 / math.sqrt(fan_in), generator=g)
+    return SpeechTokenizer(m.to(dtype=dtype))

@@ -185,6 +185,8 @@ class Engine:
         self.H = talker["hidden_size"]
         self._keep = {}  # tensors borrowed by the engine for the duration of a request
         self.loaded = False
+        self.time_kernels = False   # bench: CUDA-event time of every decode_chunk launch
+        self.last_kernel_ms = None
 
     def __del__(self):
         try:
@@ -284,7 +286,14 @@ class Engine:
         if out is None:
             out = torch.empty(n_frames, 16, dtype=torch.long, device=self.device)
         res = ChunkResult()
+        if self.time_kernels:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
         _check(self.lib, self.lib.fq3_decode_chunk(self.h, int(n_frames), out.data_ptr(), C.byref(res), self._stream()))
+        if self.time_kernels:
+            e1.record()
+            e1.synchronize()
+            self.last_kernel_ms = e0.elapsed_time(e1)
         return out[: res.frames_emitted], res
 
     def past_hidden(self) -> torch.Tensor:

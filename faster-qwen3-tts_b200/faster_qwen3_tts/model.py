@@ -1,0 +1,436 @@
+"""FasterQwen3TTS -- the reference's public wrapper (faster_qwen3_tts/model.py:21-1505) over the B200 engine.
+
+Kept verbatim from the reference: constructor signature, ``from_pretrained`` / ``warmup`` / ``_warmup`` /
+``generate`` / ``generate_voice_clone[_streaming]`` / ``generate_custom_voice[_streaming]`` /
+``generate_voice_design[_streaming]`` names, positional order, keyword defaults, return shapes, error types, the
+``speech_tokenizer`` / ``sample_rate`` surface, and the streaming codec-window policy (model.py:1052-1135).
+
+Replaced: the two graph objects are thin handles on one fq3 engine (persistent sm_100a kernel); per-chunk work
+is one kernel launch + one codec decode.
+
+Prompt assembly (tokeniser, speaker encoder, ICL prompt; model.py:295-805) is upstream ``qwen-tts`` code that is
+absent from this image; with a synthetic base model (``from_synthetic``) a deterministic stand-in builds prompt
+embeddings of the documented shapes.  With a real upstream model the upstream helpers are called through
+``_prepare_generation_upstream`` (next row, not accelerated here).
+"""
+from __future__ import annotations
+
+import hashlib
+import logging
+import time
+from pathlib import Path
+from typing import Any, Dict, Generator, List, Optional, Tuple, Union
+
+import numpy as np
+import torch
+
+logger = logging.getLogger(__name__)
+
+CONTEXT_FRAMES = 25  # model.py:1056
+
+
+class FasterQwen3TTS:
+    def __init__(self, base_model, predictor_graph, talker_graph, device: str = "cuda",
+                 dtype: torch.dtype = torch.bfloat16, max_seq_len: int = 2048):
+        self.model = base_model
+        self.predictor_graph = predictor_graph
+        self.talker_graph = talker_graph
+        self.device = device
+        self.dtype = dtype
+        self.max_seq_len = max_seq_len
+        self.sample_rate = self._infer_sample_rate(base_model)
+        self._warmed_up = False
+        self._voice_prompt_cache = {}
+
+    # ------------------------------------------------------------------ small surface kept from the reference
+    @staticmethod
+    def _get_speech_tokenizer(base_model):
+        return getattr(getattr(base_model, "model", None), "speech_tokenizer", None)
+
+    @property
+    def speech_tokenizer(self):
+        st = self._get_speech_tokenizer(self.model)
+        if st is None:
+            raise AttributeError("Underlying model does not expose a speech_tokenizer")
+        return st
+
+    @property
+    def engine(self):
+        return getattr(self.talker_graph, "engine", None)
+
+    @staticmethod
+    def _infer_sample_rate(base_model) -> int:
+        sr = None
+        st = FasterQwen3TTS._get_speech_tokenizer(base_model)
+        if st is not None:
+            sr = getattr(st, "sample_rate", None)
+        if sr is None:
+            sr = getattr(base_model, "sample_rate", None)
+        if sr is None:
+            logger.warning("Could not infer sample rate from base model; defaulting to 24000 Hz.")
+            return 24000
+        return int(sr)
+
+    @staticmethod
+    def _resolve_non_streaming_mode(non_streaming_mode: Optional[bool], *, default: bool) -> bool:
+        return default if non_streaming_mode is None else non_streaming_mode
+
+    @staticmethod
+    def _reject_ggml_cached_reference_args(ref_spk, ref_rvq, ref_spk_emb, ref_codes) -> None:
+        if any(v is not None for v in (ref_spk, ref_rvq, ref_spk_emb, ref_codes)):
+            raise NotImplementedError(
+                "ref_spk/ref_rvq cached qwentts.cpp references require backend='ggml'. "
+                "Use voice_clone_prompt for precomputed prompts with the torch backend.")
+
+    # ------------------------------------------------------------------ construction
+    @classmethod
+    def from_pretrained(cls, model_name: str, device: str = "cuda", dtype: Union[str, torch.dtype] = torch.bfloat16,
+                        attn_implementation: str = "sdpa", max_seq_len: int = 2048, backend: str = "torch",
+                        quant: str = "BF16", gguf_talker_path=None, gguf_codec_path=None, qwentts_library_path=None,
+                        qwentts_use_fa: bool = True, qwentts_clamp_fp16: bool = False, qwentts_ref_cache_dir=None,
+                        cache_dir=None, local_files_only: bool = False):
+        if backend not in ("torch", "ggml", "qwentts"):
+            raise ValueError(f"Unsupported backend {backend!r}. Expected 'torch', 'ggml', or 'qwentts'.")
+        if backend in ("ggml", "qwentts"):
+            raise NotImplementedError("the qwentts.cpp / GGML adapter is out of scope of the B200 engine "
+                                      "(SURVEY.md section 2 row 9); use backend='torch'")
+        if isinstance(dtype, str):
+            dtype = getattr(torch, dtype)
+        if not device.startswith("cuda") or not torch.cuda.is_available():
+            raise ValueError("CUDA graphs require CUDA device")
+        if str(model_name).startswith("synthetic:"):
+            return cls.from_synthetic(str(model_name).split(":", 1)[1], device=device, dtype=dtype, max_seq_len=max_seq_len)
+        try:
+            from qwen_tts import Qwen3TTSModel
+        except ImportError as ex:
+            raise ImportError("qwen-tts is required to load real checkpoints; use model_name='synthetic:1.7B' "
+                              "for random-init weights of the real geometry") from ex
+        base = Qwen3TTSModel.from_pretrained(model_name, device_map=device, torch_dtype=dtype,
+                                             attn_implementation=attn_implementation)
+        return cls._wrap(base, device, dtype, max_seq_len)
+
+    @classmethod
+    def _wrap(cls, base_model, device, dtype, max_seq_len, num_ctas: int = 0):
+        from .predictor_graph import PredictorGraph
+        from .talker_graph import TalkerGraph
+        from .weights import engine_for_talker
+        talker = base_model.model.talker
+        tcfg = base_model.model.config.talker_config
+        engine = engine_for_talker(talker, dtype=dtype, device=device, max_seq_len=max_seq_len, num_ctas=num_ctas)
+        pg = PredictorGraph(talker.code_predictor, talker.code_predictor.model.config, tcfg.hidden_size, device=device,
+                            dtype=dtype, do_sample=True, top_k=50, temperature=0.9, engine=engine)
+        tg = TalkerGraph(talker.model, tcfg, device=device, dtype=dtype, max_seq_len=max_seq_len, engine=engine)
+        return cls(base_model, pg, tg, device=device, dtype=dtype, max_seq_len=max_seq_len)
+
+    @classmethod
+    def from_synthetic(cls, size: str = "1.7B", device: str = "cuda", dtype: torch.dtype = torch.bfloat16,
+                       max_seq_len: int = 2048, seed: int = 0, num_ctas: int = 0, with_codec: bool = True,
+                       codec_config=None):
+        """Random-init weights at the real geometry (no checkpoint exists offline)."""
+        from . import synthetic
+        from .codec import build_codec
+        cfg = synthetic.make_config(size)
+        st = build_codec(codec_config, seed=seed + 1, dtype=dtype, device=device) if with_codec else None
+        base = synthetic.build_base_model(cfg, None, seed=seed, dtype=dtype, device=device, speech_tokenizer=st)
+        base.syn_cfg = cfg
+        m = cls._wrap(base, device, dtype, max_seq_len, num_ctas=num_ctas)
+        return m
+
+    def warmup(self, prefill_len: int = 100) -> None:
+        if self._warmed_up:
+            return
+        self.predictor_graph.capture(num_warmup=3)
+        self.talker_graph.capture(prefill_len=prefill_len, num_warmup=3)
+        self._warmed_up = True
+
+    def _warmup(self, prefill_len: int) -> None:
+        self.warmup(prefill_len=prefill_len)
+
+    def generate(self, text: str, language: str = "English", max_new_tokens: int = 2048, temperature: float = 0.9,
+                 top_k: int = 50, do_sample: bool = True, repetition_penalty: float = 1.05) -> Tuple[list, int]:
+        raise NotImplementedError("Default voice generation not yet implemented. "
+                                  "Use generate_voice_clone() with reference audio.")
+
+    def codec_launches(self) -> int:
+        st = self._get_speech_tokenizer(self.model)
+        return int(getattr(st, "launches", 0)) if st is not None else 0
+
+    # ------------------------------------------------------------------ prompt assembly
+    def _is_synthetic(self) -> bool:
+        return bool(getattr(self.model, "synthetic", False))
+
+    def _synthetic_prompt(self, text: str, ref_text: str, icl: bool, non_streaming_mode: bool, ref_frames: int = 174):
+        """Deterministic stand-in for model.py:583-805: shapes follow SURVEY.md 8(d) (prefix ~9, ICL prompt spans the
+        reference frames, text is fed step by step unless non_streaming_mode)."""
+        cfg = self.model.syn_cfg
+        H = cfg.talker_config.hidden_size
+        n_text = max(1, len(text.split()) * 2)
+        seed = int.from_bytes(hashlib.sha256((text + "|" + ref_text).encode()).digest()[:4], "little")
+        g = torch.Generator().manual_seed(seed)
+        P = 9 + (ref_frames if icl else 1) + (n_text if non_streaming_mode else 0)
+        Tt = 0 if non_streaming_mode else n_text
+        dev = self.engine.device
+        tie = torch.randn(1, P, H, generator=g).to(self.dtype)
+        tth = torch.randn(1, max(Tt, 1), H, generator=g).to(self.dtype)[:, :Tt]
+        tpe = torch.randn(1, 1, H, generator=g).to(self.dtype)
+        ref_codes = torch.randint(0, 2048, (ref_frames, 16), generator=g) if icl else None
+        return (tie.to(dev), torch.ones(1, P, dtype=torch.long, device=dev), tth.to(dev), tpe.to(dev),
+                None if ref_codes is None else ref_codes.to(dev))
+
+    def _prepare_generation(self, text, ref_audio=None, ref_text="", language="English", xvec_only=False,
+                            non_streaming_mode=False, append_silence=True, voice_clone_prompt=None, instruct=None):
+        m = self.model.model
+        if self._is_synthetic():
+            icl = not xvec_only and (ref_audio is not None or (voice_clone_prompt or {}).get("ref_code") is not None)
+            if voice_clone_prompt is None and ref_audio is None:
+                raise ValueError("ref_audio is required when voice_clone_prompt is not provided")
+            tie, tam, tth, tpe, ref_codes = self._synthetic_prompt(text, ref_text, icl, non_streaming_mode)
+        else:
+            tie, tam, tth, tpe, ref_codes = self._prepare_generation_upstream(
+                text, ref_audio, ref_text, language, xvec_only, non_streaming_mode, append_silence, voice_clone_prompt,
+                instruct)
+        if not self._warmed_up:
+            self.warmup(tie.shape[1])
+        talker = m.talker
+        talker.rope_deltas = None
+        return m, talker, m.config.talker_config, tie, tam, tth, tpe, ref_codes
+
+    def _prepare_generation_upstream(self, *a, **k):
+        raise NotImplementedError(
+            "prompt assembly against upstream qwen-tts (model.py:295-805 of the reference) is not part of the "
+            "accelerated hot path and cannot be exercised offline; see SURVEY.md section 8(f) item 1")
+
+    def _prepare_generation_custom(self, text, language, speaker, instruct=None, non_streaming_mode=True):
+        m = self.model.model
+        if not self._is_synthetic():
+            self._prepare_generation_upstream()
+        tie, tam, tth, tpe, _ = self._synthetic_prompt(text + "|" + str(speaker) + "|" + str(instruct), "", False,
+                                                       non_streaming_mode)
+        if not self._warmed_up:
+            self.warmup(tie.shape[1])
+        m.talker.rope_deltas = None
+        return m, m.talker, m.config.talker_config, tie, tam, tth, tpe
+
+    # ------------------------------------------------------------------ codec helpers
+    @staticmethod
+    def _to_numpy(a):
+        if hasattr(a, "cpu"):
+            return a.flatten().float().cpu().numpy()
+        return a.flatten() if hasattr(a, "flatten") else a
+
+    def _decode_all(self, speech_tokenizer, codec_ids, ref_codes):
+        """Non-streaming decode + proportional reference trim (model.py:918-938)."""
+        if ref_codes is not None:
+            codes = torch.cat([ref_codes.to(codec_ids.device), codec_ids], dim=0)
+        else:
+            codes = codec_ids
+        audio_list, sr = speech_tokenizer.decode({"audio_codes": codes.unsqueeze(0)})
+        ref_len = ref_codes.shape[0] if ref_codes is not None else 0
+        out = []
+        for a in audio_list:
+            a = self._to_numpy(a)
+            if ref_len > 0:
+                a = a[int(ref_len / max(codes.shape[0], 1) * len(a)):]
+            out.append(a)
+        return out, sr
+
+    def _stream_audio(self, chunks, speech_tokenizer, ref_codes, chunk_size, to_host=True):
+        """The reference's hybrid streaming decode (model.py:1052-1135): Phase 1 re-decodes everything so far
+        (reference codes prepended in ICL mode) until max(25, chunk_size) frames exist and calibrates
+        samples_per_frame; Phase 2 decodes a 25-frame left-context window and trims the context."""
+        min_cal = max(CONTEXT_FRAMES, chunk_size)
+        all_codes, prev_len, spf = [], 0, None
+        conv = self._to_numpy if to_host else (lambda a: a.flatten())
+        for codec_chunk, timing in chunks:
+            all_codes.append(codec_chunk)
+            n_new = codec_chunk.shape[0]
+            flat = torch.cat(all_codes, dim=0)
+            n_total = flat.shape[0]
+            if spf is None:
+                inp = torch.cat([ref_codes.to(flat.device), flat], dim=0) if ref_codes is not None else flat
+                audio_list, sr = speech_tokenizer.decode({"audio_codes": inp.unsqueeze(0)})
+                audio = conv(audio_list[0])
+                if ref_codes is not None:
+                    cut = int(ref_codes.shape[0] / max(inp.shape[0], 1) * len(audio))
+                    gen_audio = audio[cut:]
+                else:
+                    gen_audio = audio
+                new_audio = gen_audio[prev_len:]
+                prev_len = len(gen_audio)
+                if n_total >= min_cal:
+                    spf = len(gen_audio) / n_total
+            else:
+                start = max(0, n_total - n_new - CONTEXT_FRAMES)
+                window = flat[start:]
+                n_ctx = window.shape[0] - n_new
+                audio_list, sr = speech_tokenizer.decode({"audio_codes": window.unsqueeze(0)})
+                audio = conv(audio_list[0])
+                new_audio = audio[int(round(n_ctx * spf)):] if n_ctx > 0 else audio
+            yield new_audio, sr, timing
+
+    def _gen_kwargs(self, max_new_tokens, min_new_tokens, temperature, top_k, top_p, do_sample, repetition_penalty):
+        return dict(max_new_tokens=max_new_tokens, min_new_tokens=min_new_tokens, temperature=temperature, top_k=top_k,
+                    top_p=top_p, do_sample=do_sample, repetition_penalty=repetition_penalty,
+                    predictor_graph=self.predictor_graph, talker_graph=self.talker_graph)
+
+    # ------------------------------------------------------------------ the embeddings-in entry (bench / servers)
+    @torch.inference_mode()
+    def stream_from_embeds(self, tie, tam, tth, tpe, ref_codes=None, chunk_size: int = 8, to_host: bool = True,
+                           max_new_tokens: int = 2048, min_new_tokens: int = 2, temperature: float = 0.9,
+                           top_k: int = 50, top_p: float = 1.0, do_sample: bool = True,
+                           repetition_penalty: float = 1.05, uniforms=None):
+        """generate_voice_clone_streaming from the point where the prompt embeddings exist (model.py:1079-1137)."""
+        from .streaming import fast_generate_streaming
+        m = self.model.model
+        m.talker.rope_deltas = None
+        chunks = fast_generate_streaming(
+            talker=m.talker, talker_input_embeds=tie, attention_mask=tam, trailing_text_hiddens=tth, tts_pad_embed=tpe,
+            config=m.config.talker_config, chunk_size=chunk_size, uniforms=uniforms,
+            **self._gen_kwargs(max_new_tokens, min_new_tokens, temperature, top_k, top_p, do_sample, repetition_penalty))
+        st = m.speech_tokenizer
+        if st is None:
+            for codes, timing in chunks:
+                yield (codes.cpu().numpy() if to_host else codes), self.sample_rate, timing
+            return
+        yield from self._stream_audio(chunks, st, ref_codes, chunk_size, to_host=to_host)
+
+    # ------------------------------------------------------------------ voice clone
+    @torch.inference_mode()
+    def generate_voice_clone(self, text: str, language: str, ref_audio=None, ref_text: str = "",
+                             max_new_tokens: int = 2048, min_new_tokens: int = 2, temperature: float = 0.9,
+                             top_k: int = 50, top_p: float = 1.0, do_sample: bool = True,
+                             repetition_penalty: float = 1.05, xvec_only: bool = False,
+                             non_streaming_mode: Optional[bool] = None, append_silence: bool = True,
+                             instruct: Optional[str] = None, ref_spk=None, ref_rvq=None, ref_spk_emb=None,
+                             ref_codes=None, voice_clone_prompt=None) -> Tuple[list, int]:
+        self._reject_ggml_cached_reference_args(ref_spk, ref_rvq, ref_spk_emb, ref_codes)
+        from .generate import fast_generate
+        nsm = self._resolve_non_streaming_mode(non_streaming_mode, default=False)
+        m, talker, config, tie, tam, tth, tpe, ref_codes = self._prepare_generation(
+            text=text, language=language, ref_audio=ref_audio, ref_text=ref_text, xvec_only=xvec_only,
+            non_streaming_mode=nsm, append_silence=append_silence, voice_clone_prompt=voice_clone_prompt,
+            instruct=instruct)
+        codec_ids, timing = fast_generate(
+            talker=talker, talker_input_embeds=tie, attention_mask=tam, trailing_text_hiddens=tth, tts_pad_embed=tpe,
+            config=config, **self._gen_kwargs(max_new_tokens, min_new_tokens, temperature, top_k, top_p, do_sample,
+                                              repetition_penalty))
+        if codec_ids is None:
+            logger.warning("Generation returned no tokens")
+            return [np.zeros(1, dtype=np.float32)], self.sample_rate
+        audio, sr = self._decode_all(m.speech_tokenizer, codec_ids, ref_codes)
+        self._log_rtf(timing)
+        return audio, sr
+
+    @torch.inference_mode()
+    def generate_voice_clone_streaming(self, text: str, language: str, ref_audio=None, ref_text: str = "",
+                                       max_new_tokens: int = 2048, min_new_tokens: int = 2, temperature: float = 0.9,
+                                       top_k: int = 50, top_p: float = 1.0, do_sample: bool = True,
+                                       repetition_penalty: float = 1.05, chunk_size: int = 12,
+                                       xvec_only: bool = False, non_streaming_mode: Optional[bool] = None,
+                                       append_silence: bool = True, parity_mode: bool = False,
+                                       instruct: Optional[str] = None, ref_spk=None, ref_rvq=None, ref_spk_emb=None,
+                                       ref_codes=None, voice_clone_prompt=None
+                                       ) -> Generator[Tuple[np.ndarray, int, dict], None, None]:
+        self._reject_ggml_cached_reference_args(ref_spk, ref_rvq, ref_spk_emb, ref_codes)
+        if parity_mode:
+            raise NotImplementedError("parity_mode streams through upstream qwen-tts's dynamic-cache generate, which "
+                                      "is absent offline")
+        nsm = self._resolve_non_streaming_mode(non_streaming_mode, default=False)
+        m, talker, config, tie, tam, tth, tpe, ref_codes = self._prepare_generation(
+            text=text, language=language, ref_audio=ref_audio, ref_text=ref_text, xvec_only=xvec_only,
+            non_streaming_mode=nsm, append_silence=append_silence, voice_clone_prompt=voice_clone_prompt,
+            instruct=instruct)
+        yield from self.stream_from_embeds(tie, tam, tth, tpe, ref_codes=ref_codes, chunk_size=chunk_size,
+                                           max_new_tokens=max_new_tokens, min_new_tokens=min_new_tokens,
+                                           temperature=temperature, top_k=top_k, top_p=top_p, do_sample=do_sample,
+                                           repetition_penalty=repetition_penalty)
+
+    # ------------------------------------------------------------------ custom voice / voice design
+    def _require_type(self, kind: str, msg: str):
+        t = getattr(self.model.model, "tts_model_type", None)
+        if t is not None and t != kind:
+            raise ValueError(msg)
+        if t is None and not self._is_synthetic():
+            raise ValueError(msg)
+
+    def _simple(self, prep_text, speaker, instruct, language, nsm_default, non_streaming_mode, gen):
+        nsm = self._resolve_non_streaming_mode(non_streaming_mode, default=nsm_default)
+        m, talker, config, tie, tam, tth, tpe = self._prepare_generation_custom(
+            text=prep_text, language=language, speaker=speaker, instruct=instruct, non_streaming_mode=nsm)
+        return m, talker, config, tie, tam, tth, tpe
+
+    @torch.inference_mode()
+    def generate_custom_voice(self, text: str, speaker: str, language: str, instruct: Optional[str] = None,
+                              non_streaming_mode: Optional[bool] = None, max_new_tokens: int = 2048,
+                              min_new_tokens: int = 2, temperature: float = 0.9, top_k: int = 50, top_p: float = 1.0,
+                              do_sample: bool = True, repetition_penalty: float = 1.05) -> Tuple[list, int]:
+        self._require_type("custom_voice", "Loaded model does not support custom voice generation")
+        from .generate import fast_generate
+        m, talker, config, tie, tam, tth, tpe = self._simple(text, speaker, instruct, language, True,
+                                                              non_streaming_mode, None)
+        codec_ids, timing = fast_generate(
+            talker=talker, talker_input_embeds=tie, attention_mask=tam, trailing_text_hiddens=tth, tts_pad_embed=tpe,
+            config=config, **self._gen_kwargs(max_new_tokens, min_new_tokens, temperature, top_k, top_p, do_sample,
+                                              repetition_penalty))
+        if codec_ids is None:
+            return [np.zeros(1, dtype=np.float32)], self.sample_rate
+        audio, sr = self._decode_all(m.speech_tokenizer, codec_ids, None)
+        self._log_rtf(timing)
+        return audio, sr
+
+    @torch.inference_mode()
+    def generate_custom_voice_streaming(self, text: str, speaker: str, language: str, instruct: Optional[str] = None,
+                                        non_streaming_mode: Optional[bool] = None, max_new_tokens: int = 2048,
+                                        min_new_tokens: int = 2, temperature: float = 0.9, top_k: int = 50,
+                                        top_p: float = 1.0, do_sample: bool = True, repetition_penalty: float = 1.05,
+                                        chunk_size: int = 12) -> Generator[Tuple[np.ndarray, int, dict], None, None]:
+        self._require_type("custom_voice", "Loaded model does not support custom voice generation")
+        m, talker, config, tie, tam, tth, tpe = self._simple(text, speaker, instruct, language, True,
+                                                              non_streaming_mode, None)
+        yield from self.stream_from_embeds(tie, tam, tth, tpe, ref_codes=None, chunk_size=chunk_size,
+                                           max_new_tokens=max_new_tokens, min_new_tokens=min_new_tokens,
+                                           temperature=temperature, top_k=top_k, top_p=top_p, do_sample=do_sample,
+                                           repetition_penalty=repetition_penalty)
+
+    @torch.inference_mode()
+    def generate_voice_design(self, text: str, instruct: str, language: str,
+                              non_streaming_mode: Optional[bool] = None, max_new_tokens: int = 2048,
+                              min_new_tokens: int = 2, temperature: float = 0.9, top_k: int = 50, top_p: float = 1.0,
+                              do_sample: bool = True, repetition_penalty: float = 1.05) -> Tuple[list, int]:
+        self._require_type("voice_design", "Loaded model does not support voice design generation")
+        return self._design_impl(text, instruct, language, non_streaming_mode, max_new_tokens, min_new_tokens,
+                                 temperature, top_k, top_p, do_sample, repetition_penalty)
+
+    def _design_impl(self, text, instruct, language, non_streaming_mode, max_new_tokens, min_new_tokens, temperature,
+                     top_k, top_p, do_sample, repetition_penalty):
+        from .generate import fast_generate
+        m, talker, config, tie, tam, tth, tpe = self._simple(text, None, instruct, language, True, non_streaming_mode,
+                                                              None)
+        codec_ids, timing = fast_generate(
+            talker=talker, talker_input_embeds=tie, attention_mask=tam, trailing_text_hiddens=tth, tts_pad_embed=tpe,
+            config=config, **self._gen_kwargs(max_new_tokens, min_new_tokens, temperature, top_k, top_p, do_sample,
+                                              repetition_penalty))
+        if codec_ids is None:
+            return [np.zeros(1, dtype=np.float32)], self.sample_rate
+        return self._decode_all(m.speech_tokenizer, codec_ids, None)
+
+    @torch.inference_mode()
+    def generate_voice_design_streaming(self, text: str, instruct: str, language: str,
+                                        non_streaming_mode: Optional[bool] = None, max_new_tokens: int = 2048,
+                                        min_new_tokens: int = 2, temperature: float = 0.9, top_k: int = 50,
+                                        top_p: float = 1.0, do_sample: bool = True, repetition_penalty: float = 1.05,
+                                        chunk_size: int = 12) -> Generator[Tuple[np.ndarray, int, dict], None, None]:
+        self._require_type("voice_design", "Loaded model does not support voice design generation")
+        m, talker, config, tie, tam, tth, tpe = self._simple(text, None, instruct, language, True, non_streaming_mode,
+                                                              None)
+        yield from self.stream_from_embeds(tie, tam, tth, tpe, ref_codes=None, chunk_size=chunk_size,
+                                           max_new_tokens=max_new_tokens, min_new_tokens=min_new_tokens,
+                                           temperature=temperature, top_k=top_k, top_p=top_p, do_sample=do_sample,
+                                           repetition_penalty=repetition_penalty)
+
+    def _log_rtf(self, timing):
+        n = timing["steps"]
+        total = timing["prefill_ms"] / 1000 + timing["decode_s"]
+        if total > 0:
+            logger.info(f"Generated {n / 12.0:.2f}s audio in {total:.2f}s ({timing['ms_per_step']:.1f}ms/step, "
+                        f"RTF: {n / 12.0 / total:.2f})")

@@ -56,7 +56,10 @@ def fast_generate_streaming(
             n = res.frames_emitted
             if n:
                 total += n
-                yield codes.clone(), _timing(idx, n, t_prefill, time.time() - t1, total, n < chunk_size)
+                tm = _timing(idx, n, t_prefill, time.time() - t1, total, n < chunk_size)
+                if engine.time_kernels:
+                    tm["kernel_ms"] = engine.last_kernel_ms
+                yield codes.clone(), tm
                 idx += 1
                 t1 = time.time()
             if res.finished:

@@ -189,24 +189,28 @@ class Talker(nn.Module):
 def build_base_model(cfg, state: Optional[Dict[str, torch.Tensor]] = None, *, seed: int = 0, dtype=torch.bfloat16,
                      device="cpu", speech_tokenizer=None, std: float = 0.02):
     """Module tree with weights from `state` (HF-style names, see oracle.make_weights) or seeded N(0, std^2)."""
-    talker = Talker(cfg)
+    dev = torch.device(device)
+    with torch.device(dev):
+        talker = Talker(cfg)
+    for prm in talker.parameters():
+        prm.requires_grad_(False)
     if state is not None:
         sd = {k[len("talker."):]: v for k, v in state.items() if k.startswith("talker.")}
         missing, unexpected = talker.load_state_dict(sd, strict=False)
         assert not unexpected, unexpected
         assert not missing, missing
     else:
-        g = torch.Generator().manual_seed(seed)
+        g = torch.Generator(device=dev).manual_seed(seed)
         for name, p in talker.named_parameters():
             if name.endswith("norm.weight") or "layernorm" in name:
                 p.fill_(1.0)
             elif "codec_embedding" in name:
-                p.copy_(torch.randn(p.shape, generator=g))
+                p.normal_(0.0, 1.0, generator=g)
             elif "codec_head" in name or "lm_head" in name:
-                p.copy_(torch.randn(p.shape, generator=g) * std * 4)
+                p.normal_(0.0, std * 4, generator=g)
             else:
-                p.copy_(torch.randn(p.shape, generator=g) * std)
-    talker = talker.to(device=device, dtype=dtype)
+                p.normal_(0.0, std, generator=g)
+    talker = talker.to(dtype=dtype)
     inner = types.SimpleNamespace(talker=talker, config=types.SimpleNamespace(talker_config=cfg.talker_config),
                                   speech_tokenizer=speech_tokenizer)
     return types.SimpleNamespace(model=inner, synthetic=True)

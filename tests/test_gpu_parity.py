@@ -195,10 +195,11 @@ def test_reference_scheduler_drives_engine_duck_types(tiny32):
     p = tiny32
     p.pg.do_sample = False
     tie, tth, tpe = O.make_inputs(p.cfg, 9, 3, seed=1)
-    rows = [r for k, r in stepwise_frames(
-        p.talker, tie[None].cuda(), torch.ones(1, 9, dtype=torch.long).cuda(), tth[None].cuda(), tpe[None, None].cuda(),
-        p.config, p.pg, p.tg, max_new_tokens=10, min_new_tokens=2, temperature=0.9, top_k=50, top_p=1.0,
-        do_sample=False, repetition_penalty=1.05) if k == "frame"]
+    with torch.inference_mode():
+        rows = [r for k, r in stepwise_frames(
+            p.talker, tie[None].cuda(), torch.ones(1, 9, dtype=torch.long).cuda(), tth[None].cuda(),
+            tpe[None, None].cuda(), p.config, p.pg, p.tg, max_new_tokens=10, min_new_tokens=2, temperature=0.9,
+            top_k=50, top_p=1.0, do_sample=False, repetition_penalty=1.05) if k == "frame"]
     with torch.inference_mode():
         want = O.generate(p.om, tie, tth, tpe, max_new_tokens=10,
                           sp_talker=O.SamplingParams(do_sample=False, repetition_penalty=1.05),
