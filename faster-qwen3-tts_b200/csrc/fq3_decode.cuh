@@ -39,7 +39,7 @@ constexpr int MAXGRP = 512;          // row groups per CTA
 constexpr int MAXSEG = 256;          // GEMV segments
 constexpr int SEQMAX = 4096;
 
-enum Mode { MODE_FUSED = 0, MODE_TALKER_STEP = 1, MODE_PRED_RUN = 2 };
+enum Mode { MODE_FUSED = 0, MODE_TALKER_STEP = 1, MODE_PRED_RUN = 2, MODE_BARRIER_TEST = 3 };
 
 struct Grp {           // one row group of one segment, as seen by one CTA (<= 32 rows, full K)
   uint32_t off16;      // tape offset / 16
@@ -214,6 +214,36 @@ __device__ __forceinline__ void grid_sync(Ctx& c) {
   csync();
 }
 
+// experimental variants measured by tools/microbench.py (MODE_BARRIER_TEST)
+__device__ __forceinline__ void grid_sync_v1(Ctx& c) {  // release-reduction + acquire-poll, no separate fences
+  csync();
+  if (c.tid == 0) {
+    c.bar_target += (unsigned)c.P.ncta;
+    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(c.P.bar), "r"(1u) : "memory");
+    while (ld_acquire_u32(c.P.bar) < c.bar_target) {
+    }
+  }
+  csync();
+}
+__device__ __forceinline__ void grid_sync_v2(Ctx& c) {  // two-level: 16 group counters (128 B apart) + top counter
+  csync();
+  if (c.tid == 0) {
+    const unsigned ng = 16;
+    const unsigned grp = blockIdx.x % ng;
+    const unsigned gsize = (c.P.ncta - grp + ng - 1) / ng;
+    c.bar_target += 1;  // epoch
+    unsigned* gc = c.P.bar + 32 * (1 + grp);
+    unsigned old;
+    asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], %2;" : "=r"(old) : "l"(gc), "r"(1u) : "memory");
+    if (old + 1 == gsize * c.bar_target)
+      asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(c.P.bar), "r"(1u) : "memory");
+    const unsigned want = ng < (unsigned)c.P.ncta ? ng : (unsigned)c.P.ncta;
+    while (ld_acquire_u32(c.P.bar) < want * c.bar_target) {
+    }
+  }
+  csync();
+}
+
 __device__ __forceinline__ float block_sum(Ctx& c, float v) {
 #pragma unroll
   for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -235,6 +265,15 @@ __device__ __forceinline__ float block_max(Ctx& c, float v) {
   for (int w = 1; w < NCW; ++w) r = fmaxf(r, c.s.red[w]);
   csync();
   return r;
+}
+
+// timing probe (dbg_on & 2): CTA 0 / thread 0 appends clock64() to the tail of the debug buffer
+__device__ __forceinline__ void probe(Ctx& c, int& idx) {
+  if ((c.P.dbg_on & 2) && blockIdx.x == 0 && c.tid == 0) {
+    long long* ts = reinterpret_cast<long long*>(c.P.dbg);
+    if (idx < 4096) ts[idx] = clock64();
+  }
+  idx++;
 }
 
 // RMSNorm (transformers Qwen3 RMSNorm: fp32 variance, x*rsqrt(var+eps) -> dtype, weight * that) of a global fp32
@@ -816,7 +855,10 @@ __device__ void run_layers(Ctx& c, const StackDev& S, int nt, int slot0, int rpo
                            bool dbg, bool is_talker) {
   const KParams& P = c.P;
   const bool cta0 = blockIdx.x == 0;
+  int pi = 0;
+  dbg = dbg && (P.dbg_on & 1);
   for (int l = 0; l < S.L; ++l) {
+    probe(c, pi);  // 0: layer start
     // ---- P1: input norm + QKV rows
     for (int t = 0; t < nt; ++t) {
       if (l == 0 && x0_local)
@@ -824,6 +866,7 @@ __device__ void run_layers(Ctx& c, const StackDev& S, int nt, int slot0, int rpo
       else
         norm_to_smem<BF>(c, P.X + (size_t)t * P.ldX, S.ln_in, (size_t)l * S.H, S.H, S.eps, c.s.xs + t * S.H);
     }
+    probe(c, pi);  // 1: after input norm
     {
       auto epi = [&](int row, const float* v0, const float* v1) {
         for (int t = 0; t < nt; ++t) {
@@ -834,7 +877,9 @@ __device__ void run_layers(Ctx& c, const StackDev& S, int nt, int slot0, int rpo
       if (nt == 1) gemv_seg<BF, 1>(c, S.seg_base + 4 * l + 0, c.s.xs, S.H, epi);
       else gemv_seg<BF, 2>(c, S.seg_base + 4 * l + 0, c.s.xs, S.H, epi);
     }
+    probe(c, pi);  // 2: after QKV gemv
     grid_sync(c);
+    probe(c, pi);  // 3: after B1
     if (dbg && cta0) {
       float* d = P.dbg + (size_t)l * P.dbg_stride_layer;
       for (int t = 0; t < nt; ++t)
@@ -842,7 +887,9 @@ __device__ void run_layers(Ctx& c, const StackDev& S, int nt, int slot0, int rpo
     }
     // ---- P2: attention, one q-head per CTA
     for (int h = blockIdx.x; h < S.nH; h += gridDim.x) attention_head<BF>(c, S, l, h, nt, slot0, rpos0, kv_start);
+    probe(c, pi);  // 4: after attention
     grid_sync(c);
+    probe(c, pi);  // 5: after B2
     // ---- P3: o_proj + residual
     for (int t = 0; t < nt; ++t)
       for (int k = c.tid; k < S.qd; k += NCT) c.s.xs[t * S.qd + k] = __ldcg(P.ATT + (size_t)t * P.ldATT + k);
@@ -864,7 +911,9 @@ __device__ void run_layers(Ctx& c, const StackDev& S, int nt, int slot0, int rpo
       if (nt == 1) gemv_seg<BF, 1>(c, S.seg_base + 4 * l + 1, c.s.xs, S.qd, epi);
       else gemv_seg<BF, 2>(c, S.seg_base + 4 * l + 1, c.s.xs, S.qd, epi);
     }
+    probe(c, pi);  // 6: after O gemv
     grid_sync(c);
+    probe(c, pi);  // 7: after B3
     // ---- P4: post-attention norm + gate/up rows (interleaved pairs) + SiLU*up
     for (int t = 0; t < nt; ++t)
       norm_to_smem<BF>(c, P.X1 + (size_t)t * P.ldX, S.ln_post, (size_t)l * S.H, S.H, S.eps, c.s.xs + t * S.H);
@@ -884,7 +933,9 @@ __device__ void run_layers(Ctx& c, const StackDev& S, int nt, int slot0, int rpo
       if (nt == 1) gemv_seg<BF, 1>(c, S.seg_base + 4 * l + 2, c.s.xs, S.H, epi);
       else gemv_seg<BF, 2>(c, S.seg_base + 4 * l + 2, c.s.xs, S.H, epi);
     }
+    probe(c, pi);  // 8: after GU gemv
     grid_sync(c);
+    probe(c, pi);  // 9: after B4
     // ---- P5: down rows + residual
     for (int t = 0; t < nt; ++t)
       for (int k = c.tid; k < S.I; k += NCT) c.s.xs[t * S.I + k] = __ldcg(P.ACT + (size_t)t * P.ldACT + k);
@@ -904,7 +955,9 @@ __device__ void run_layers(Ctx& c, const StackDev& S, int nt, int slot0, int rpo
       if (nt == 1) gemv_seg<BF, 1>(c, S.seg_base + 4 * l + 3, c.s.xs, S.I, epi);
       else gemv_seg<BF, 2>(c, S.seg_base + 4 * l + 3, c.s.xs, S.I, epi);
     }
+    probe(c, pi);  // 10: after DN gemv
     grid_sync(c);
+    probe(c, pi);  // 11: after B5
     if (dbg && cta0) {
       float* d = P.dbg + (size_t)l * P.dbg_stride_layer + (size_t)2 * (S.qd + 2 * S.kd) + 2 * S.qd + 2 * S.H + 2 * S.I;
       for (int t = 0; t < nt; ++t)
@@ -961,7 +1014,7 @@ __device__ void predictor_frame(Ctx& c, const float* u15, bool dbg) {
       x0_local = true;
     }
     const int slot0 = (i == 0) ? 0 : i + 1;
-    run_layers<BF>(c, S, nt, slot0, slot0, 0, x0_local, dbg && i == 0, false);
+    run_layers<BF>(c, S, nt, slot0, slot0, 0, x0_local, dbg && i == 1, false);
     head_logits<BF>(c, S.seg_head + i, S.H);
     SampleArgs sa;
     sa.logits = P.LOGITS; sa.V = S.V; sa.sp = P.sp_p; sa.u = u15 ? __ldg(u15 + i) : 0.f;
@@ -1007,7 +1060,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) fq3_decode_kernel(const __grid_co
     // ======================================= PRODUCER =======================================
     if (lane == 0) {
       Producer pr{P, s, 0u, false};
-      if (P.mode == MODE_TALKER_STEP) {
+      if (P.mode == MODE_BARRIER_TEST) {
+      } else if (P.mode == MODE_TALKER_STEP) {
         pr.stack_layers(P.t);
       } else {
         const int iters = P.mode == MODE_FUSED ? P.n_frames : 1;
@@ -1031,7 +1085,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) fq3_decode_kernel(const __grid_co
     // ======================================= CONSUMERS ======================================
     Ctx c{P, s, tid, warp, lane, 0u, 0u};
     const int Ht = P.t.H;
-    if (P.mode == MODE_TALKER_STEP) {
+    if (P.mode == MODE_BARRIER_TEST) {
+      for (int i = 0; i < P.n_frames; ++i) {
+        if (P.position == 0) grid_sync(c);
+        else if (P.position == 1) grid_sync_v1(c);
+        else grid_sync_v2(c);
+      }
+    } else if (P.mode == MODE_TALKER_STEP) {
       for (int k = tid; k < Ht; k += NCT) s.xin[0][k] = ldw<BF>(P.in_embeds, k);
       csync();
       run_layers<BF>(c, P.t, 1, P.position, P.position + P.rope_delta, P.n_left_pad, true, P.dbg_on != 0, true);

@@ -226,7 +226,7 @@ extern "C" int fq3_engine_create(const fq3_config* cfg, fq3_engine** out) {
   CK(cudaMalloc(&e->X, 2 * ldX * sizeof(float))); CK(cudaMalloc(&e->X1, 2 * ldX * sizeof(float)));
   CK(cudaMalloc(&e->QKV, 2 * ldQKV * sizeof(float))); CK(cudaMalloc(&e->ATT, 2 * ldATT * sizeof(float)));
   CK(cudaMalloc(&e->ACT, 2 * ldACT * sizeof(float))); CK(cudaMalloc(&e->LOGITS, VMAX * sizeof(float)));
-  CK(cudaMalloc(&e->bar, 256)); CK(cudaMemset(e->bar, 0, 256));
+  CK(cudaMalloc(&e->bar, 4096)); CK(cudaMemset(e->bar, 0, 4096));
   CK(cudaMalloc(&e->state, 64)); CK(cudaMemset(e->state, 0, 64));
   CK(cudaMallocHost(&e->state_host, 64));
   CK(cudaMalloc(&e->past_hidden, HMAX * sizeof(float))); CK(cudaMemset(e->past_hidden, 0, HMAX * sizeof(float)));
@@ -532,7 +532,7 @@ extern "C" int fq3_engine_load_weights(fq3_engine* e, const fq3_tensor* tensors,
 // launches
 // ------------------------------------------------------------------------------------------------------------
 static int launch_decode(fq3_engine* e, const KParams& kp, cudaStream_t stream) {
-  CK(cudaMemsetAsync(e->bar, 0, 4, stream));
+  CK(cudaMemsetAsync(e->bar, 0, 4096, stream));
   void* args[] = {(void*)&kp};
   if (e->bf16)
     CK(cudaLaunchCooperativeKernel((const void*)fq3_decode_kernel<true>, dim3(e->ncta), dim3(NTHREADS), args, smem_bytes(), stream));
@@ -675,9 +675,19 @@ extern "C" int fq3_get_past_hidden(fq3_engine* e, void* dst_dev, void* stream_) 
   return 0;
 }
 
+extern "C" int fq3_barrier_test(fq3_engine* e, int32_t n, int32_t kind, void* stream_) {
+  if (!e || !e->loaded) return fail(FQ3_ERR_STATE, "weights not loaded");
+  CK(cudaSetDevice(e->dev));
+  KParams kp = e->kp;
+  kp.mode = MODE_BARRIER_TEST;
+  kp.n_frames = n;
+  kp.position = kind;
+  return launch_decode(e, kp, (cudaStream_t)stream_);
+}
+
 extern "C" int fq3_debug_enable(fq3_engine* e, int32_t on) {
   if (!e) return fail(FQ3_ERR_INVALID, "null argument");
-  e->dbg_on = on ? 1 : 0;
+  e->dbg_on = on;
   return 0;
 }
 

@@ -61,7 +61,7 @@ EXPORTS = [
     "fq3_engine_create", "fq3_engine_load_weights", "fq3_engine_destroy", "fq3_import_kv",
     "fq3_set_generation_state", "fq3_talker_step", "fq3_predictor_run", "fq3_sample_logits", "fq3_begin_request",
     "fq3_decode_chunk", "fq3_get_past_hidden", "fq3_debug_enable", "fq3_debug_read", "fq3_tape_bytes",
-    "fq3_num_ctas", "fq3_launch_count", "fq3_last_error", "fq3_version",
+    "fq3_num_ctas", "fq3_launch_count", "fq3_last_error", "fq3_version", "fq3_barrier_test",
 ]
 
 
@@ -114,6 +114,7 @@ def load_library() -> C.CDLL:
     lib.fq3_debug_read.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]
     lib.fq3_tape_bytes.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     lib.fq3_num_ctas.argtypes = [C.c_void_p]
+    lib.fq3_barrier_test.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
     if hasattr(lib, "fq3_codec_create"):
         lib.fq3_codec_create.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
         lib.fq3_codec_destroy.argtypes = [C.c_void_p]
@@ -302,7 +303,8 @@ class Engine:
         return out
 
     # -- introspection ----------------------------------------------------------------------------------------
-    def debug_enable(self, on: bool):
+    def debug_enable(self, on):
+        """bit 0: dump per-layer intermediates; bit 1: clock64 probes of CTA 0 (tools/microbench.py)."""
         _check(self.lib, self.lib.fq3_debug_enable(self.h, int(on)))
 
     def debug_layers(self, which: str, nt: int) -> Dict[str, torch.Tensor]:
@@ -327,6 +329,14 @@ class Engine:
             out[f"L{l}.act"] = r[o:o + nt * I].view(nt, I); o += 2 * I
             out[f"L{l}.x"] = r[o:o + 2 * H].view(2, H)[:nt]
         return out
+
+    def probe_timestamps(self, n: int) -> torch.Tensor:
+        buf = torch.empty(2 * n, dtype=torch.float32)
+        _check(self.lib, self.lib.fq3_debug_read(self.h, 0, buf.numel(), buf.data_ptr()))
+        return buf.view(torch.int64)
+
+    def barrier_test(self, n: int, kind: int):
+        _check(self.lib, self.lib.fq3_barrier_test(self.h, int(n), int(kind), self._stream()))
 
     def tape_bytes(self) -> Tuple[int, int]:
         a, b = C.c_int64(), C.c_int64()
