@@ -25,6 +25,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 namespace fq3 {
 
 constexpr int NCW = 8;               // consumer warps
@@ -99,6 +101,8 @@ struct KParams {
   float* dbg;
   int dbg_on;
   long long dbg_stride_layer;  // floats per layer record
+  int pred_pin_layers;         // predictor layers whose weights are streamed with L2 evict_last
+  int mma_tape;                // 1: bf16 tensor-core fragment layout, 0: fp32 row-chunk layout
 };
 
 // ------------------------------------------------------------------------------------------------------------
@@ -135,6 +139,13 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                    smem_u32(dst)),
                "l"(src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_hint(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t pol) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+          smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
+      : "memory");
 }
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
   unsigned v;
@@ -201,7 +212,7 @@ struct Ctx {
 // ------------------------------------------------------------------------------------------------------------
 // grid barrier (consumer warps of all CTAs).  The producer warp never waits here.
 // ------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void grid_sync(Ctx& c) {
+__device__ __forceinline__ void grid_sync_v0(Ctx& c) {  // fence + relaxed atomic + fence (cooperative-groups style)
   csync();
   if (c.tid == 0) {
     c.bar_target += (unsigned)c.P.ncta;
@@ -210,6 +221,17 @@ __device__ __forceinline__ void grid_sync(Ctx& c) {
     while (ld_acquire_u32(c.P.bar) < c.bar_target) {
     }
     __threadfence();
+  }
+  csync();
+}
+// default: bar.sync orders the CTA's writes before thread 0's release-reduction (cumulativity); pollers acquire.
+__device__ __forceinline__ void grid_sync(Ctx& c) {
+  csync();
+  if (c.tid == 0) {
+    c.bar_target += (unsigned)c.P.ncta;
+    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(c.P.bar), "r"(1u) : "memory");
+    while (ld_acquire_u32(c.P.bar) < c.bar_target) {
+    }
   }
   csync();
 }
@@ -279,32 +301,41 @@ __device__ __forceinline__ void probe(Ctx& c, int& idx) {
 // RMSNorm (transformers Qwen3 RMSNorm: fp32 variance, x*rsqrt(var+eps) -> dtype, weight * that) of a global fp32
 // vector into shared memory.  Every CTA computes it redundantly.
 template <bool BF>
-__device__ __forceinline__ void norm_to_smem(Ctx& c, const float* src, const void* w, size_t woff, int H, float eps,
-                                             float* dst) {
-  float ss = 0.f;
-  for (int k = c.tid; k < H; k += NCT) {
-    float v = __ldcg(src + k);
-    dst[k] = v;
-    ss += v * v;
+__device__ __forceinline__ void norm_any(Ctx& c, const float* src, bool src_smem, const void* w, size_t woff, int H,
+                                         float eps, float* dst) {
+  constexpr int MAXE = HMAX / NCT;
+  float v[MAXE], wv[MAXE];
+#pragma unroll
+  for (int i = 0; i < MAXE; ++i) {
+    const int k = c.tid + i * NCT;
+    v[i] = 0.f;
+    wv[i] = 0.f;
+    if (k < H) {
+      v[i] = src_smem ? src[k] : __ldcg(src + k);
+      wv[i] = ldw<BF>(w, woff + k);  // issued together with the activation loads: one memory round trip
+    }
   }
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXE; ++i) ss += v[i] * v[i];
   ss = block_sum(c, ss);
   const float r = 1.0f / sqrtf(ss / (float)H + eps);
-  for (int k = c.tid; k < H; k += NCT) dst[k] = rnd<BF>(ldw<BF>(w, woff + k) * rnd<BF>(dst[k] * r));
+#pragma unroll
+  for (int i = 0; i < MAXE; ++i) {
+    const int k = c.tid + i * NCT;
+    if (k < H) dst[k] = rnd<BF>(wv[i] * rnd<BF>(v[i] * r));
+  }
   csync();
 }
-// same, source already in shared memory (layer 0 input held locally)
+template <bool BF>
+__device__ __forceinline__ void norm_to_smem(Ctx& c, const float* src, const void* w, size_t woff, int H, float eps,
+                                             float* dst) {
+  norm_any<BF>(c, src, false, w, woff, H, eps, dst);
+}
 template <bool BF>
 __device__ __forceinline__ void norm_smem_to_smem(Ctx& c, const float* src, const void* w, size_t woff, int H,
                                                   float eps, float* dst) {
-  float ss = 0.f;
-  for (int k = c.tid; k < H; k += NCT) {
-    float v = src[k];
-    ss += v * v;
-  }
-  ss = block_sum(c, ss);
-  const float r = 1.0f / sqrtf(ss / (float)H + eps);
-  for (int k = c.tid; k < H; k += NCT) dst[k] = rnd<BF>(ldw<BF>(w, woff + k) * rnd<BF>(src[k] * r));
-  csync();
+  norm_any<BF>(c, src, true, w, woff, H, eps, dst);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -403,13 +434,15 @@ struct Producer {
   Smem& s;
   uint32_t ctr;
   bool stopped;
-  __device__ __forceinline__ void seg(int sg) {
+  uint64_t pol_first, pol_last;  // L2 eviction policies: stream-once weights vs weights re-read 15x per frame
+  __device__ __forceinline__ void seg(int sg, bool keep = false) {
     if (stopped) return;
     const uint32_t st = s.seg[sg];
     const int gbeg = (int)(st >> 8), gn = (int)(st & 255u);
     for (int gi = 0; gi < gn; ++gi) {
       const Grp g = s.grp[gbeg + gi];
-      const uint32_t bytes = (uint32_t)g.rows * g.m * 512u;
+      // fp32 tape: rows x m x 512-byte row chunks; bf16 tape: n_mt x G k-groups x 2048-byte fragment blocks
+      const uint32_t bytes = P.mma_tape ? (uint32_t)(g.rows & 0xff) * g.m * 2048u : (uint32_t)g.rows * g.m * 512u;
       const uint8_t* src = P.tape + (size_t)g.off16 * 16;
       for (int tl = 0; tl < g.ntiles; ++tl) {
         const int stage = (int)(ctr % NS);
@@ -425,14 +458,14 @@ struct Producer {
           return;
         }
         mbar_expect_tx(&s.full[stage], bytes);
-        bulk_g2s(s.ring[stage], src + (size_t)tl * bytes, bytes, &s.full[stage]);
+        bulk_g2s_hint(s.ring[stage], src + (size_t)tl * bytes, bytes, &s.full[stage], keep ? pol_last : pol_first);
         ++ctr;
       }
     }
   }
-  __device__ __forceinline__ void stack_layers(const StackDev& S) {
+  __device__ __forceinline__ void stack_layers(const StackDev& S, int keep_layers = 0) {
     for (int l = 0; l < S.L; ++l)
-      for (int q = 0; q < 4; ++q) seg(S.seg_base + 4 * l + q);
+      for (int q = 0; q < 4; ++q) seg(S.seg_base + 4 * l + q, l < keep_layers);
   }
 };
 
@@ -461,28 +494,34 @@ __device__ void attention_head(Ctx& c, const StackDev& S, int layer, int h, int 
   if (c.warp < 3 * nt) {
     const int t = c.warp / 3, what = c.warp % 3;
     const float* src = P.QKV + (size_t)t * P.ldQKV + (what == 0 ? h * 128 : (what == 1 ? S.qd + g * 128 : S.qd + S.kd + g * 128));
-    float v[4];
+    float v[4], nwv[4], cc[4], sv[4];
+    {
+      int rp = rpos0 + t;
+      rp = rp < 0 ? 0 : (rp >= S.npos ? S.npos - 1 : rp);
+      const float* cs = S.cos + (size_t)rp * 128;
+      const float* sn = S.sin + (size_t)rp * 128;
+      const void* nw = what == 0 ? S.qnorm : S.knorm;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) v[i] = __ldcg(src + c.lane + 32 * i);
+      for (int i = 0; i < 4; ++i) {  // all global loads of this step issued back to back
+        const int e = c.lane + 32 * i;
+        v[i] = __ldcg(src + e);
+        nwv[i] = what < 2 ? ldw<BF>(nw, (size_t)layer * 128 + e) : 0.f;
+        cc[i] = what < 2 ? __ldg(cs + e) : 0.f;
+        sv[i] = what < 2 ? __ldg(sn + e) : 0.f;
+      }
+    }
     if (what < 2) {
       float ss = v[0] * v[0] + v[1] * v[1] + v[2] * v[2] + v[3] * v[3];
 #pragma unroll
       for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
       const float r = 1.0f / sqrtf(ss / 128.0f + S.eps);
-      const void* nw = what == 0 ? S.qnorm : S.knorm;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) v[i] = rnd<BF>(ldw<BF>(nw, (size_t)layer * 128 + c.lane + 32 * i) * rnd<BF>(v[i] * r));
-      int rp = rpos0 + t;
-      rp = rp < 0 ? 0 : (rp >= S.npos ? S.npos - 1 : rp);
-      const float* cs = S.cos + (size_t)rp * 128;
-      const float* sn = S.sin + (size_t)rp * 128;
+      for (int i = 0; i < 4; ++i) v[i] = rnd<BF>(nwv[i] * rnd<BF>(v[i] * r));
       float o[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const int e = c.lane + 32 * i;
-        const float cc = rnd<BF>(__ldg(cs + e)), sv = rnd<BF>(__ldg(sn + e));
         const float rot = (i < 2) ? -v[i + 2] : v[i - 2];
-        o[i] = rnd<BF>(rnd<BF>(v[i] * cc) + rnd<BF>(rot * sv));
+        o[i] = rnd<BF>(rnd<BF>(v[i] * rnd<BF>(cc[i])) + rnd<BF>(rot * rnd<BF>(sv[i])));
       }
 #pragma unroll
       for (int i = 0; i < 4; ++i) v[i] = o[i];
@@ -568,24 +607,24 @@ __device__ void attention_head(Ctx& c, const StackDev& S, int layer, int h, int 
     sm = block_sum(c, sm);
     for (int j = c.tid; j < nk; j += NCT) sct[j] = rnd<BF>(sct[j] / sm);
     csync();
-    // --- d. P.V : warp w takes keys w, w+8, ...; lane owns dims [4*lane, 4*lane+4)
+    // --- d. P.V : 16-byte loads; bf16: 16 lanes per key (lane owns 8 dims), 2 keys per warp instruction
     {
+      constexpr int LPK = BF ? 16 : 32;
+      constexpr int KPW = 32 / LPK;
+      constexpr int EPL = BF ? 8 : 4;
       constexpr int U = 8;
-      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-      for (int base = c.warp; base < nold; base += NCW * U) {
-        float pv[U];
+      const int sub = c.lane % LPK, kin = c.lane / LPK;
+      float acc[EPL];
+#pragma unroll
+      for (int e = 0; e < EPL; ++e) acc[e] = 0.f;
+      for (int base = 0; base < nold; base += NCW * KPW * U) {
         uint4 vv[U];
+        float pv[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-          const int jj = base + u * NCW;
+          const int jj = base + (u * NCW + c.warp) * KPW + kin;
           if (jj < nold) {
-            const uint8_t* row = vbase + ((size_t)(kv_start + jj) * 128) * esz;
-            if constexpr (BF) {
-              const uint2 w2 = __ldcg(reinterpret_cast<const uint2*>(row) + c.lane);
-              vv[u] = make_uint4(w2.x, w2.y, 0, 0);
-            } else {
-              vv[u] = __ldcg(reinterpret_cast<const uint4*>(row) + c.lane);
-            }
+            vv[u] = __ldcg(reinterpret_cast<const uint4*>(vbase + ((size_t)(kv_start + jj) * 128) * esz) + sub);
             pv[u] = sct[jj];
           } else {
             vv[u] = make_uint4(0, 0, 0, 0);
@@ -595,25 +634,32 @@ __device__ void attention_head(Ctx& c, const StackDev& S, int layer, int h, int 
 #pragma unroll
         for (int u = 0; u < U; ++u) {
           if constexpr (BF) {
-            a0 = fmaf(pv[u], bf_lo(vv[u].x), a0); a1 = fmaf(pv[u], bf_hi(vv[u].x), a1);
-            a2 = fmaf(pv[u], bf_lo(vv[u].y), a2); a3 = fmaf(pv[u], bf_hi(vv[u].y), a3);
+            acc[0] = fmaf(pv[u], bf_lo(vv[u].x), acc[0]); acc[1] = fmaf(pv[u], bf_hi(vv[u].x), acc[1]);
+            acc[2] = fmaf(pv[u], bf_lo(vv[u].y), acc[2]); acc[3] = fmaf(pv[u], bf_hi(vv[u].y), acc[3]);
+            acc[4] = fmaf(pv[u], bf_lo(vv[u].z), acc[4]); acc[5] = fmaf(pv[u], bf_hi(vv[u].z), acc[5]);
+            acc[6] = fmaf(pv[u], bf_lo(vv[u].w), acc[6]); acc[7] = fmaf(pv[u], bf_hi(vv[u].w), acc[7]);
           } else {
-            a0 = fmaf(pv[u], __uint_as_float(vv[u].x), a0); a1 = fmaf(pv[u], __uint_as_float(vv[u].y), a1);
-            a2 = fmaf(pv[u], __uint_as_float(vv[u].z), a2); a3 = fmaf(pv[u], __uint_as_float(vv[u].w), a3);
+            acc[0] = fmaf(pv[u], __uint_as_float(vv[u].x), acc[0]); acc[1] = fmaf(pv[u], __uint_as_float(vv[u].y), acc[1]);
+            acc[2] = fmaf(pv[u], __uint_as_float(vv[u].z), acc[2]); acc[3] = fmaf(pv[u], __uint_as_float(vv[u].w), acc[3]);
           }
         }
       }
-      if (c.warp == 0) {
+      if constexpr (BF) {  // fold the two key halves of the warp: lanes sub and sub+16 own the same dims
+#pragma unroll
+        for (int e = 0; e < EPL; ++e) acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], 16);
+      }
+      if (c.warp == 0 && kin == 0) {
         for (int j = 0; j <= t; ++j) {
           const float pj = sct[nold + j];
-          a0 = fmaf(pj, vs[j * 128 + 4 * c.lane + 0], a0);
-          a1 = fmaf(pj, vs[j * 128 + 4 * c.lane + 1], a1);
-          a2 = fmaf(pj, vs[j * 128 + 4 * c.lane + 2], a2);
-          a3 = fmaf(pj, vs[j * 128 + 4 * c.lane + 3], a3);
+#pragma unroll
+          for (int e = 0; e < EPL; ++e) acc[e] = fmaf(pj, vs[j * 128 + sub * EPL + e], acc[e]);
         }
       }
-      float* op = opart + c.warp * 128 + 4 * c.lane;
-      op[0] = a0; op[1] = a1; op[2] = a2; op[3] = a3;
+      if (kin == 0) {
+        float* op = opart + c.warp * 128 + sub * EPL;
+#pragma unroll
+        for (int e = 0; e < EPL; ++e) op[e] = acc[e];
+      }
     }
     csync();
     if (c.tid < 128) {
@@ -847,8 +893,321 @@ __device__ int sample_block(Ctx& c, const SampleArgs& a) {
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// Tensor-core GEMV (bf16): the tape holds mma.sync m16n8k16 A-fragments in register order, so one LDS.128 per lane
+// feeds one mma (16 rows x 16 k).  The activation vector(s) sit in shared memory as bf16 and enter as the B operand
+// (column n = token; for 8-row "HALF" tiles columns 2n / 2n+1 carry the two K halves, rows 0-7 / 8-15 of the tile
+// hold the matching halves of the weight rows, and c0 + c3 is the full dot product).  Warps split the k-groups of a
+// tile; partial accumulators are combined in shared memory in a fixed order.
+//   pre(row, tok) -> float   value fetched BEFORE streaming starts (residual), handed back to epi
+//   epi(row, tok, v, vup, aux)   GU tiles: row = pair index, v = gate, vup = up
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mma_bf16(float* d, const uint4& a, uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b0), "r"(b1));
+}
+
+template <int NT, class Pre, class Epi>
+__device__ __forceinline__ void gemv_mma(Ctx& c, int seg, int K, Pre pre, Epi epi) {
+  const __nv_bfloat16* xh = reinterpret_cast<const __nv_bfloat16*>(c.s.xs);
+  float* red = c.s.xs + XS_FLOATS / 2;  // [NCW][2][4][32] partial accumulators
+  const uint32_t st = c.s.seg[seg];
+  const int gbeg = (int)(st >> 8), gn = (int)(st & 255u);
+  const int gq = c.lane >> 2, t = c.lane & 3;
+  for (int gi = 0; gi < gn; ++gi) {
+    const Grp g = c.s.grp[gbeg + gi];
+    const int n_mt = g.rows & 0xff, kind = g.rows >> 8, G = g.m;
+    int tok, koff;
+    bool bvalid;
+    if (kind == 1) { tok = gq >> 1; koff = (gq & 1) * (K >> 1); bvalid = gq < 2 * NT; }
+    else { tok = gq; koff = 0; bvalid = gq < NT; }
+    const __nv_bfloat16* xb = xh + (bvalid ? tok * K + koff : 0) + 16 * t;
+    float aux[4] = {0.f, 0.f, 0.f, 0.f};
+    if (c.warp < n_mt) {
+      if (kind == 0) {
+        const int rA = g.row0 + c.warp * 16 + gq;
+        if (2 * t < NT) { aux[0] = pre(rA, 2 * t); aux[2] = pre(rA + 8, 2 * t); }
+        if (2 * t + 1 < NT) { aux[1] = pre(rA, 2 * t + 1); aux[3] = pre(rA + 8, 2 * t + 1); }
+      } else if (kind == 1) {
+        if (t < NT) aux[0] = pre(g.row0 + gq, t);
+      }
+    }
+    float acc[2][4];
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int r = 0; r < 4; ++r) acc[a][r] = 0.f;
+    for (int tl = 0; tl < g.ntiles; ++tl) {
+      const int stage = (int)(c.tile_ctr % NS);
+      const uint32_t par = (c.tile_ctr / NS) & 1u;
+      mbar_wait(&c.s.full[stage], par);
+      const uint8_t* tile = c.s.ring[stage];
+      for (int qq = c.warp; qq < G; qq += NCW) {
+        const int kg = tl * G + qq;
+        uint4 blo = make_uint4(0, 0, 0, 0), bhi = make_uint4(0, 0, 0, 0);
+        if (bvalid) {
+          blo = *reinterpret_cast<const uint4*>(xb + 64 * kg);
+          bhi = *reinterpret_cast<const uint4*>(xb + 64 * kg + 8);
+        }
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+          if (mt < n_mt) {
+            const uint4* A = reinterpret_cast<const uint4*>(tile + ((size_t)(mt * G + qq) * 4) * 512) + c.lane;
+            const uint4 a0 = A[0], a1 = A[32], a2 = A[64], a3 = A[96];
+            mma_bf16(acc[mt], a0, blo.x, blo.y);
+            mma_bf16(acc[mt], a1, blo.z, blo.w);
+            mma_bf16(acc[mt], a2, bhi.x, bhi.y);
+            mma_bf16(acc[mt], a3, bhi.z, bhi.w);
+          }
+        }
+      }
+      __syncwarp();
+      if (c.lane == 0) mbar_arrive(&c.s.empty[stage]);
+      c.tile_ctr++;
+    }
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+      if (mt < n_mt)
+#pragma unroll
+        for (int r = 0; r < 4; ++r) red[((c.warp * 2 + mt) * 4 + r) * 32 + c.lane] = acc[mt][r];
+    csync();
+    if (c.warp < n_mt) {
+      const int mt = c.warp;
+      float cv[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        float sm = 0.f;
+#pragma unroll
+        for (int w = 0; w < NCW; ++w) sm += red[((w * 2 + mt) * 4 + r) * 32 + c.lane];
+        cv[r] = sm;
+      }
+      if (kind == 2) {
+        const int pair = g.row0 + mt * 8 + gq;
+        if (2 * t < NT) epi(pair, 2 * t, cv[0], cv[2], 0.f);
+        if (2 * t + 1 < NT) epi(pair, 2 * t + 1, cv[1], cv[3], 0.f);
+      } else if (kind == 0) {
+        const int rA = g.row0 + mt * 16 + gq;
+        if (2 * t < NT) { epi(rA, 2 * t, cv[0], 0.f, aux[0]); epi(rA + 8, 2 * t, cv[2], 0.f, aux[2]); }
+        if (2 * t + 1 < NT) { epi(rA, 2 * t + 1, cv[1], 0.f, aux[1]); epi(rA + 8, 2 * t + 1, cv[3], 0.f, aux[3]); }
+      } else {
+        if (t < NT) epi(g.row0 + gq, t, cv[0] + cv[3], 0.f, aux[0]);
+      }
+    }
+    csync();
+  }
+}
+
+// dispatch: bf16 -> tensor-core path on the bf16 staging vector, fp32 -> FMA path on the fp32 staging vector
+template <bool BF, bool GU, class Pre, class Epi>
+__device__ __forceinline__ void gemv_any(Ctx& c, int seg, int nt, int K, Pre pre, Epi epi) {
+  if constexpr (BF) {
+    if (nt == 1) gemv_mma<1>(c, seg, K, pre, epi);
+    else gemv_mma<2>(c, seg, K, pre, epi);
+  } else {
+    auto epi2 = [&](int row0, const float* v0, const float* v1) {
+      for (int t = 0; t < nt; ++t) {
+        if constexpr (GU) {
+          epi(row0 >> 1, t, v0[t], v1[t], 0.f);
+        } else {
+          epi(row0, t, v0[t], 0.f, pre(row0, t));
+          epi(row0 + 1, t, v1[t], 0.f, pre(row0 + 1, t));
+        }
+      }
+    };
+    if (nt == 1) gemv_seg<false, 1>(c, seg, c.s.xs, K, epi2);
+    else gemv_seg<false, 2>(c, seg, c.s.xs, K, epi2);
+  }
+}
+
+// staging vector element store: bf16 array (tensor-core path) or fp32 array (fp32 parity mode), both in s.xs
+template <bool BF>
+__device__ __forceinline__ void xs_put(Ctx& c, int idx, float v) {
+  if constexpr (BF) reinterpret_cast<__nv_bfloat16*>(c.s.xs)[idx] = __float2bfloat16_rn(v);
+  else c.s.xs[idx] = v;
+}
+template <bool BF>
+__device__ __forceinline__ float xs_get(Ctx& c, int idx) {
+  if constexpr (BF) return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(c.s.xs)[idx]);
+  else return c.s.xs[idx];
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Predictor-size attention (cache <= 32 slots, i.e. <= 17 keys): EVERY CTA computes all heads redundantly from the
+// QKV scratch and the tiny KV cache and writes the result straight into the staging vector that feeds o_proj.
+// This removes the attention exchange (ATT round trip) and one grid barrier per layer.  One warp per kv group;
+// a lane owns dims [4*lane, 4*lane+4) of every 128-vector; CTA 0 appends the new K/V to the cache.
+// ------------------------------------------------------------------------------------------------------------
+template <bool BF>
+__device__ void attention_small_all(Ctx& c, const StackDev& S, int layer, int nt, int slot0, int rpos0) {
+  const KParams& P = c.P;
+  constexpr int MAXK = 18;
+  const float scale = 0.08838834764831845f;
+  const size_t esz = BF ? 2 : 4;
+  const int L4 = 4 * c.lane;
+  for (int g = c.warp; g < S.nKV; g += NCW) {
+    const uint8_t* kb = reinterpret_cast<const uint8_t*>(S.kc) + ((size_t)(layer * S.nKV + g) * S.S * 128) * esz;
+    const uint8_t* vb = reinterpret_cast<const uint8_t*>(S.vc) + ((size_t)(layer * S.nKV + g) * S.S * 128) * esz;
+    // ---- issue every global load up front: old K/V rows (kept packed: 16 bytes fp32 / 8 bytes bf16 per lane)
+    using Raw = typename std::conditional<BF, uint2, float4>::type;
+    Raw kraw[16], vraw[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      if (j < slot0) {
+        kraw[j] = __ldcg(reinterpret_cast<const Raw*>(kb + (size_t)j * 128 * esz) + c.lane);
+        vraw[j] = __ldcg(reinterpret_cast<const Raw*>(vb + (size_t)j * 128 * esz) + c.lane);
+      } else {
+        if constexpr (BF) { kraw[j] = make_uint2(0, 0); vraw[j] = make_uint2(0, 0); }
+        else { kraw[j] = make_float4(0, 0, 0, 0); vraw[j] = make_float4(0, 0, 0, 0); }
+      }
+    }
+    auto unpack = [](const Raw& r, float* o) {
+      if constexpr (BF) { o[0] = bf_lo(r.x); o[1] = bf_hi(r.x); o[2] = bf_lo(r.y); o[3] = bf_hi(r.y); }
+      else { o[0] = r.x; o[1] = r.y; o[2] = r.z; o[3] = r.w; }
+    };
+    float qn[4], kn[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      qn[i] = ldw<BF>(S.qnorm, (size_t)layer * 128 + L4 + i);
+      kn[i] = ldw<BF>(S.knorm, (size_t)layer * 128 + L4 + i);
+    }
+    float knew[2][4], vnew[2][4];
+    // rms-norm + rope of one 128-vector held as 4 dims per lane (pairs d, d+64 live in lanes l, l^16)
+    auto norm_rope = [&](float* v, const float* w, int rp) {
+      float ss = v[0] * v[0] + v[1] * v[1] + v[2] * v[2] + v[3] * v[3];
+#pragma unroll
+      for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+      const float r = 1.0f / sqrtf(ss / 128.0f + S.eps);
+      rp = rp < 0 ? 0 : (rp >= S.npos ? S.npos - 1 : rp);
+      float o4[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) v[i] = rnd<BF>(w[i] * rnd<BF>(v[i] * r));
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float other = __shfl_xor_sync(0xffffffffu, v[i], 16);
+        const float rot = c.lane < 16 ? -other : other;
+        const float cc = rnd<BF>(__ldg(S.cos + (size_t)rp * 128 + L4 + i)), sv = rnd<BF>(__ldg(S.sin + (size_t)rp * 128 + L4 + i));
+        o4[i] = rnd<BF>(rnd<BF>(v[i] * cc) + rnd<BF>(rot * sv));
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) v[i] = o4[i];
+    };
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+      if (t < nt) {
+      const float4 kr = __ldcg(reinterpret_cast<const float4*>(P.QKV + (size_t)t * P.ldQKV + S.qd + g * 128) + c.lane);
+      const float4 vr = __ldcg(reinterpret_cast<const float4*>(P.QKV + (size_t)t * P.ldQKV + S.qd + S.kd + g * 128) + c.lane);
+      knew[t][0] = kr.x; knew[t][1] = kr.y; knew[t][2] = kr.z; knew[t][3] = kr.w;
+      vnew[t][0] = vr.x; vnew[t][1] = vr.y; vnew[t][2] = vr.z; vnew[t][3] = vr.w;
+      norm_rope(knew[t], kn, rpos0 + t);
+      if (blockIdx.x == 0) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          stw<BF>(const_cast<uint8_t*>(kb) + (size_t)(slot0 + t) * 128 * esz, L4 + i, knew[t][i]);
+          stw<BF>(const_cast<uint8_t*>(vb) + (size_t)(slot0 + t) * 128 * esz, L4 + i, vnew[t][i]);
+        }
+      }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { knew[t][i] = 0.f; vnew[t][i] = 0.f; }
+      }
+    }
+    for (int hh = 0; hh < S.rep; ++hh) {
+      const int h = g * S.rep + hh;
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        if (t < nt) {
+        const float4 qr = __ldcg(reinterpret_cast<const float4*>(P.QKV + (size_t)t * P.ldQKV + h * 128) + c.lane);
+        float q[4] = {qr.x, qr.y, qr.z, qr.w};
+        norm_rope(q, qn, rpos0 + t);
+        const int nk = slot0 + t + 1;  // visible keys: cache slots [0, slot0) then new tokens 0..t
+        float sc[MAXK];
+#pragma unroll
+        for (int j = 0; j < MAXK; ++j) {
+          float d = 0.f;
+          if (j < 16) {
+            float kf[4];
+            unpack(kraw[j], kf);
+            d = q[0] * kf[0];
+            d = fmaf(q[1], kf[1], d); d = fmaf(q[2], kf[2], d); d = fmaf(q[3], kf[3], d);
+          }
+          // new keys occupy positions slot0 .. slot0+t
+          if (j == slot0) { d = q[0] * knew[0][0]; d = fmaf(q[1], knew[0][1], d); d = fmaf(q[2], knew[0][2], d); d = fmaf(q[3], knew[0][3], d); }
+          if (nt == 2 && j == slot0 + 1) { d = q[0] * knew[1][0]; d = fmaf(q[1], knew[1][1], d); d = fmaf(q[2], knew[1][2], d); d = fmaf(q[3], knew[1][3], d); }
+#pragma unroll
+          for (int o = 16; o; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+          sc[j] = j < nk ? rnd<BF>(rnd<BF>(d) * scale) : -INFINITY;
+        }
+        float mx = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < MAXK; ++j) mx = fmaxf(mx, sc[j]);
+        float sm = 0.f;
+#pragma unroll
+        for (int j = 0; j < MAXK; ++j) {
+          sc[j] = j < nk ? expf(sc[j] - mx) : 0.f;
+          sm += sc[j];
+        }
+        float o4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int j = 0; j < MAXK; ++j) {
+          const float pj = rnd<BF>(sc[j] / sm);
+          if (j < 16) {
+            float vf[4];
+            unpack(vraw[j], vf);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) o4[i] = fmaf(pj, j < slot0 ? vf[i] : 0.f, o4[i]);
+          }
+          if (j == slot0) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) o4[i] = fmaf(pj, vnew[0][i], o4[i]);
+          }
+          if (nt == 2 && j == slot0 + 1) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) o4[i] = fmaf(pj, vnew[1][i], o4[i]);
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) xs_put<BF>(c, t * S.qd + h * 128 + L4 + i, rnd<BF>(o4[i]));
+        }
+      }
+    }
+  }
+  csync();
+}
+
+// RMSNorm of a vector (global fp32 or shared fp32) into the staging vector at element offset `off`
+template <bool BF>
+__device__ __forceinline__ void norm_stage(Ctx& c, const float* src, bool src_smem, const void* w, size_t woff, int H,
+                                           float eps, int off) {
+  constexpr int MAXE = HMAX / NCT;
+  float v[MAXE], wv[MAXE];
+#pragma unroll
+  for (int i = 0; i < MAXE; ++i) {
+    const int k = c.tid + i * NCT;
+    v[i] = 0.f;
+    wv[i] = 0.f;
+    if (k < H) {
+      v[i] = src_smem ? src[k] : __ldcg(src + k);
+      wv[i] = ldw<BF>(w, woff + k);
+    }
+  }
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXE; ++i) ss += v[i] * v[i];
+  ss = block_sum(c, ss);
+  const float r = 1.0f / sqrtf(ss / (float)H + eps);
+#pragma unroll
+  for (int i = 0; i < MAXE; ++i) {
+    const int k = c.tid + i * NCT;
+    if (k < H) xs_put<BF>(c, off + k, rnd<BF>(wv[i] * rnd<BF>(v[i] * r)));
+  }
+  csync();
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // One pass through a transformer stack for nt tokens held in X (global) or xin (shared, layer 0).
-// On return every CTA holds the final-norm hidden of the LAST token in s.xs[0..H) and X holds the residual stream.
+// On return every CTA holds the final-norm hidden of the LAST token in the staging vector [0..H) and X holds the
+// residual stream.
 // ------------------------------------------------------------------------------------------------------------
 template <bool BF>
 __device__ void run_layers(Ctx& c, const StackDev& S, int nt, int slot0, int rpos0, int kv_start, bool x0_local,
@@ -857,26 +1216,17 @@ __device__ void run_layers(Ctx& c, const StackDev& S, int nt, int slot0, int rpo
   const bool cta0 = blockIdx.x == 0;
   int pi = 0;
   dbg = dbg && (P.dbg_on & 1);
+  auto nopre = [](int, int) { return 0.f; };
   for (int l = 0; l < S.L; ++l) {
     probe(c, pi);  // 0: layer start
     // ---- P1: input norm + QKV rows
     for (int t = 0; t < nt; ++t) {
-      if (l == 0 && x0_local)
-        norm_smem_to_smem<BF>(c, c.s.xin[t], S.ln_in, (size_t)l * S.H, S.H, S.eps, c.s.xs + t * S.H);
-      else
-        norm_to_smem<BF>(c, P.X + (size_t)t * P.ldX, S.ln_in, (size_t)l * S.H, S.H, S.eps, c.s.xs + t * S.H);
+      if (l == 0 && x0_local) norm_stage<BF>(c, c.s.xin[t], true, S.ln_in, (size_t)l * S.H, S.H, S.eps, t * S.H);
+      else norm_stage<BF>(c, P.X + (size_t)t * P.ldX, false, S.ln_in, (size_t)l * S.H, S.H, S.eps, t * S.H);
     }
     probe(c, pi);  // 1: after input norm
-    {
-      auto epi = [&](int row, const float* v0, const float* v1) {
-        for (int t = 0; t < nt; ++t) {
-          P.QKV[(size_t)t * P.ldQKV + row] = rnd<BF>(v0[t]);
-          P.QKV[(size_t)t * P.ldQKV + row + 1] = rnd<BF>(v1[t]);
-        }
-      };
-      if (nt == 1) gemv_seg<BF, 1>(c, S.seg_base + 4 * l + 0, c.s.xs, S.H, epi);
-      else gemv_seg<BF, 2>(c, S.seg_base + 4 * l + 0, c.s.xs, S.H, epi);
-    }
+    gemv_any<BF, false>(c, S.seg_base + 4 * l + 0, nt, S.H, nopre,
+                        [&](int row, int t, float v, float, float) { P.QKV[(size_t)t * P.ldQKV + row] = rnd<BF>(v); });
     probe(c, pi);  // 2: after QKV gemv
     grid_sync(c);
     probe(c, pi);  // 3: after B1
@@ -885,76 +1235,84 @@ __device__ void run_layers(Ctx& c, const StackDev& S, int nt, int slot0, int rpo
       for (int t = 0; t < nt; ++t)
         for (int k = c.tid; k < S.qd + 2 * S.kd; k += NCT) d[(size_t)t * (S.qd + 2 * S.kd) + k] = __ldcg(P.QKV + (size_t)t * P.ldQKV + k);
     }
-    // ---- P2: attention, one q-head per CTA
-    for (int h = blockIdx.x; h < S.nH; h += gridDim.x) attention_head<BF>(c, S, l, h, nt, slot0, rpos0, kv_start);
-    probe(c, pi);  // 4: after attention
-    grid_sync(c);
-    probe(c, pi);  // 5: after B2
-    // ---- P3: o_proj + residual
-    for (int t = 0; t < nt; ++t)
-      for (int k = c.tid; k < S.qd; k += NCT) c.s.xs[t * S.qd + k] = __ldcg(P.ATT + (size_t)t * P.ldATT + k);
-    csync();
+    const bool small_attn = !is_talker && S.S <= 32 && slot0 + nt <= 17;
+    if (small_attn) {
+      // ---- P2+P3 fused: redundant small attention straight into the staging vector (no exchange, no barrier)
+      attention_small_all<BF>(c, S, l, nt, slot0, rpos0);
+      probe(c, pi);  // 4
+      probe(c, pi);  // 5
+    } else {
+      // ---- P2: attention, one q-head per CTA
+      for (int h = blockIdx.x; h < S.nH; h += gridDim.x) attention_head<BF>(c, S, l, h, nt, slot0, rpos0, kv_start);
+      if (is_talker && (int)blockIdx.x >= S.nH && slot0 - kv_start > 64) {
+        // idle CTAs pull the NEXT layer's keys/values into L2 (evict_last) so the attention CTAs see L2 latency
+        const int ln = (l + 1) % S.L;
+        const size_t esz = BF ? 2 : 4;
+        const int lines_per_row = (int)(128 * esz / 128);
+        const int nk = slot0 - kv_start + (ln == 0 ? 1 : 0);
+        const long long total = (long long)S.nKV * nk * lines_per_row * 2;
+        const int nidle = (int)gridDim.x - S.nH;
+        for (long long i = (long long)(blockIdx.x - S.nH) * NCT + c.tid; i < total; i += (long long)nidle * NCT) {
+          const int which = (int)(i & 1);
+          long long r = i >> 1;
+          const int ln_i = (int)(r % lines_per_row);
+          r /= lines_per_row;
+          const int j = (int)(r % nk);
+          const int g = (int)(r / nk);
+          const uint8_t* base = reinterpret_cast<const uint8_t*>(which ? S.vc : S.kc) +
+                                (((size_t)(ln * S.nKV + g) * S.S + kv_start + j) * 128) * esz + (size_t)ln_i * 128;
+          asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(base));
+        }
+      }
+      probe(c, pi);  // 4: after attention
+      grid_sync(c);
+      probe(c, pi);  // 5: after B2
+      // ---- P3: o_proj + residual
+      for (int t = 0; t < nt; ++t)
+        for (int k = c.tid; k < S.qd; k += NCT) xs_put<BF>(c, t * S.qd + k, __ldcg(P.ATT + (size_t)t * P.ldATT + k));
+      csync();
+    }
     if (dbg && cta0) {
       float* d = P.dbg + (size_t)l * P.dbg_stride_layer + (size_t)2 * (S.qd + 2 * S.kd);
-      for (int k = c.tid; k < nt * S.qd; k += NCT) d[k] = c.s.xs[k];
+      for (int k = c.tid; k < nt * S.qd; k += NCT) d[k] = xs_get<BF>(c, k);
     }
     {
       const bool loc = (l == 0 && x0_local);
-      auto epi = [&](int row, const float* v0, const float* v1) {
-        for (int t = 0; t < nt; ++t) {
-          const float r0 = loc ? c.s.xin[t][row] : __ldcg(P.X + (size_t)t * P.ldX + row);
-          const float r1 = loc ? c.s.xin[t][row + 1] : __ldcg(P.X + (size_t)t * P.ldX + row + 1);
-          P.X1[(size_t)t * P.ldX + row] = rnd<BF>(r0 + rnd<BF>(v0[t]));
-          P.X1[(size_t)t * P.ldX + row + 1] = rnd<BF>(r1 + rnd<BF>(v1[t]));
-        }
-      };
-      if (nt == 1) gemv_seg<BF, 1>(c, S.seg_base + 4 * l + 1, c.s.xs, S.qd, epi);
-      else gemv_seg<BF, 2>(c, S.seg_base + 4 * l + 1, c.s.xs, S.qd, epi);
+      gemv_any<BF, false>(
+          c, S.seg_base + 4 * l + 1, nt, S.qd,
+          [&](int row, int t) { return loc ? c.s.xin[t][row] : __ldcg(P.X + (size_t)t * P.ldX + row); },
+          [&](int row, int t, float v, float, float res) { P.X1[(size_t)t * P.ldX + row] = rnd<BF>(res + rnd<BF>(v)); });
     }
     probe(c, pi);  // 6: after O gemv
     grid_sync(c);
     probe(c, pi);  // 7: after B3
-    // ---- P4: post-attention norm + gate/up rows (interleaved pairs) + SiLU*up
+    // ---- P4: post-attention norm + gate/up rows + SiLU*up
     for (int t = 0; t < nt; ++t)
-      norm_to_smem<BF>(c, P.X1 + (size_t)t * P.ldX, S.ln_post, (size_t)l * S.H, S.H, S.eps, c.s.xs + t * S.H);
+      norm_stage<BF>(c, P.X1 + (size_t)t * P.ldX, false, S.ln_post, (size_t)l * S.H, S.H, S.eps, t * S.H);
     if (dbg && cta0) {
       float* d = P.dbg + (size_t)l * P.dbg_stride_layer + (size_t)2 * (S.qd + 2 * S.kd) + 2 * S.qd;
       for (int t = 0; t < nt; ++t)
         for (int k = c.tid; k < S.H; k += NCT) d[(size_t)t * S.H + k] = __ldcg(P.X1 + (size_t)t * P.ldX + k);
     }
-    {
-      auto epi = [&](int row, const float* v0, const float* v1) {
-        for (int t = 0; t < nt; ++t) {
-          const float gte = rnd<BF>(v0[t]), up = rnd<BF>(v1[t]);
-          const float sl = rnd<BF>(gte / (1.0f + expf(-gte)));
-          P.ACT[(size_t)t * P.ldACT + (row >> 1)] = rnd<BF>(sl * up);
-        }
-      };
-      if (nt == 1) gemv_seg<BF, 1>(c, S.seg_base + 4 * l + 2, c.s.xs, S.H, epi);
-      else gemv_seg<BF, 2>(c, S.seg_base + 4 * l + 2, c.s.xs, S.H, epi);
-    }
+    gemv_any<BF, true>(c, S.seg_base + 4 * l + 2, nt, S.H, nopre, [&](int pair, int t, float gv, float uv, float) {
+      const float gte = rnd<BF>(gv), up = rnd<BF>(uv);
+      const float sl = rnd<BF>(gte / (1.0f + expf(-gte)));
+      P.ACT[(size_t)t * P.ldACT + pair] = rnd<BF>(sl * up);
+    });
     probe(c, pi);  // 8: after GU gemv
     grid_sync(c);
     probe(c, pi);  // 9: after B4
     // ---- P5: down rows + residual
     for (int t = 0; t < nt; ++t)
-      for (int k = c.tid; k < S.I; k += NCT) c.s.xs[t * S.I + k] = __ldcg(P.ACT + (size_t)t * P.ldACT + k);
+      for (int k = c.tid; k < S.I; k += NCT) xs_put<BF>(c, t * S.I + k, __ldcg(P.ACT + (size_t)t * P.ldACT + k));
     csync();
     if (dbg && cta0) {
       float* d = P.dbg + (size_t)l * P.dbg_stride_layer + (size_t)2 * (S.qd + 2 * S.kd) + 2 * S.qd + 2 * S.H;
-      for (int k = c.tid; k < nt * S.I; k += NCT) d[k] = c.s.xs[k];
+      for (int k = c.tid; k < nt * S.I; k += NCT) d[k] = xs_get<BF>(c, k);
     }
-    {
-      auto epi = [&](int row, const float* v0, const float* v1) {
-        for (int t = 0; t < nt; ++t) {
-          const float r0 = __ldcg(P.X1 + (size_t)t * P.ldX + row), r1 = __ldcg(P.X1 + (size_t)t * P.ldX + row + 1);
-          P.X[(size_t)t * P.ldX + row] = rnd<BF>(r0 + rnd<BF>(v0[t]));
-          P.X[(size_t)t * P.ldX + row + 1] = rnd<BF>(r1 + rnd<BF>(v1[t]));
-        }
-      };
-      if (nt == 1) gemv_seg<BF, 1>(c, S.seg_base + 4 * l + 3, c.s.xs, S.I, epi);
-      else gemv_seg<BF, 2>(c, S.seg_base + 4 * l + 3, c.s.xs, S.I, epi);
-    }
+    gemv_any<BF, false>(
+        c, S.seg_base + 4 * l + 3, nt, S.I, [&](int row, int t) { return __ldcg(P.X1 + (size_t)t * P.ldX + row); },
+        [&](int row, int t, float v, float, float res) { P.X[(size_t)t * P.ldX + row] = rnd<BF>(res + rnd<BF>(v)); });
     probe(c, pi);  // 10: after DN gemv
     grid_sync(c);
     probe(c, pi);  // 11: after B5
@@ -964,20 +1322,16 @@ __device__ void run_layers(Ctx& c, const StackDev& S, int nt, int slot0, int rpo
         for (int k = c.tid; k < S.H; k += NCT) d[(size_t)t * S.H + k] = __ldcg(P.X + (size_t)t * P.ldX + k);
     }
   }
-  // final norm of the last token -> xs[0..H)
-  norm_to_smem<BF>(c, P.X + (size_t)(nt - 1) * P.ldX, S.ln_f, 0, S.H, S.eps, c.s.xs);
-  (void)is_talker;
+  // final norm of the last token -> staging vector [0..H)
+  norm_stage<BF>(c, P.X + (size_t)(nt - 1) * P.ldX, false, S.ln_f, 0, S.H, S.eps, 0);
 }
 
-// head GEMV (rows of a [V,H] matrix) on xs[0..H) -> LOGITS, then grid barrier
+// head GEMV (rows of a [V,H] matrix) on the staging vector -> LOGITS, then grid barrier
 template <bool BF>
 __device__ __forceinline__ void head_logits(Ctx& c, int seg, int H) {
   const KParams& P = c.P;
-  auto epi = [&](int row, const float* v0, const float* v1) {
-    P.LOGITS[row] = rnd<BF>(v0[0]);
-    P.LOGITS[row + 1] = rnd<BF>(v1[0]);
-  };
-  gemv_seg<BF, 1>(c, seg, c.s.xs, H, epi);
+  gemv_any<BF, false>(c, seg, 1, H, [](int, int) { return 0.f; },
+                      [&](int row, int, float v, float, float) { P.LOGITS[row] = rnd<BF>(v); });
   grid_sync(c);
 }
 
@@ -988,7 +1342,6 @@ __device__ void predictor_frame(Ctx& c, const float* u15, bool dbg) {
   const KParams& P = c.P;
   const StackDev& S = P.p;
   const int Ht = P.t.H;
-  const bool cta0 = blockIdx.x == 0;
   for (int i = 0; i < P.ncb; ++i) {
     const int nt = (i == 0) ? 2 : 1;
     if (i > 0) {
@@ -999,22 +1352,18 @@ __device__ void predictor_frame(Ctx& c, const float* u15, bool dbg) {
     }
     bool x0_local;
     if (P.has_mtp) {
-      auto epi = [&](int row, const float* v0, const float* v1) {
-        const float b0 = P.mtp_b ? ldw<BF>(P.mtp_b, row) : 0.f, b1 = P.mtp_b ? ldw<BF>(P.mtp_b, row + 1) : 0.f;
-        for (int t = 0; t < nt; ++t) {
-          P.X[(size_t)t * P.ldX + row] = rnd<BF>(v0[t] + b0);
-          P.X[(size_t)t * P.ldX + row + 1] = rnd<BF>(v1[t] + b1);
-        }
-      };
-      if (nt == 1) gemv_seg<BF, 1>(c, P.seg_mtp, &c.s.xin[0][0], HMAX, epi);
-      else gemv_seg<BF, 2>(c, P.seg_mtp, &c.s.xin[0][0], HMAX, epi);
+      for (int t = 0; t < nt; ++t)
+        for (int k = c.tid; k < Ht; k += NCT) xs_put<BF>(c, t * Ht + k, c.s.xin[t][k]);
+      csync();
+      gemv_any<BF, false>(c, P.seg_mtp, nt, Ht, [&](int row, int) { return P.mtp_b ? ldw<BF>(P.mtp_b, row) : 0.f; },
+                          [&](int row, int t, float v, float, float b) { P.X[(size_t)t * P.ldX + row] = rnd<BF>(v + b); });
       grid_sync(c);
       x0_local = false;
     } else {
       x0_local = true;
     }
     const int slot0 = (i == 0) ? 0 : i + 1;
-    run_layers<BF>(c, S, nt, slot0, slot0, 0, x0_local, dbg && i == 1, false);
+    run_layers<BF>(c, S, nt, slot0, slot0, 0, x0_local, dbg && i == 0, false);
     head_logits<BF>(c, S.seg_head + i, S.H);
     SampleArgs sa;
     sa.logits = P.LOGITS; sa.V = S.V; sa.sp = P.sp_p; sa.u = u15 ? __ldg(u15 + i) : 0.f;
@@ -1022,7 +1371,6 @@ __device__ void predictor_frame(Ctx& c, const float* u15, bool dbg) {
     const int tok = sample_block<BF>(c, sa);
     if (c.tid == 0) c.s.codes[i + 1] = tok;
     csync();
-    (void)cta0;
   }
 }
 
@@ -1059,7 +1407,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) fq3_decode_kernel(const __grid_co
   if (warp == NCW) {
     // ======================================= PRODUCER =======================================
     if (lane == 0) {
-      Producer pr{P, s, 0u, false};
+      Producer pr{P, s, 0u, false, 0ull, 0ull};
+      asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pr.pol_first));
+      asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pr.pol_last));
       if (P.mode == MODE_BARRIER_TEST) {
       } else if (P.mode == MODE_TALKER_STEP) {
         pr.stack_layers(P.t);
@@ -1067,8 +1417,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) fq3_decode_kernel(const __grid_co
         const int iters = P.mode == MODE_FUSED ? P.n_frames : 1;
         for (int f = 0; f < iters && !pr.stopped; ++f) {
           for (int i = 0; i < P.ncb; ++i) {
-            if (P.has_mtp) pr.seg(P.seg_mtp);
-            pr.stack_layers(P.p);
+            if (P.has_mtp) pr.seg(P.seg_mtp, true);
+            pr.stack_layers(P.p, P.pred_pin_layers);
             pr.seg(P.p.seg_head + i);
           }
           if (P.mode == MODE_FUSED) {
@@ -1087,7 +1437,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fq3_decode_kernel(const __grid_co
     const int Ht = P.t.H;
     if (P.mode == MODE_BARRIER_TEST) {
       for (int i = 0; i < P.n_frames; ++i) {
-        if (P.position == 0) grid_sync(c);
+        if (P.position == 0) grid_sync_v0(c);
         else if (P.position == 1) grid_sync_v1(c);
         else grid_sync_v2(c);
       }
@@ -1096,7 +1446,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fq3_decode_kernel(const __grid_co
       csync();
       run_layers<BF>(c, P.t, 1, P.position, P.position + P.rope_delta, P.n_left_pad, true, P.dbg_on != 0, true);
       if (cta == 0)
-        for (int k = tid; k < Ht; k += NCT) stw<BF>(P.hidden_out, k, s.xs[k]);
+        for (int k = tid; k < Ht; k += NCT) stw<BF>(P.hidden_out, k, xs_get<BF>(c, k));
     } else if (P.mode == MODE_PRED_RUN) {
       for (int k = tid; k < 2 * Ht; k += NCT) s.xin[k / Ht][k % Ht] = ldw<BF>(P.pred_input, k);
       csync();
@@ -1140,7 +1490,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fq3_decode_kernel(const __grid_co
         const int pos = P.prefill_len + step;
         if (pos >= P.max_seq_len - 1) { finished = 3; step++; break; }   // generate.py:175-177 (frame already emitted)
         run_layers<BF>(c, P.t, 1, pos, pos + P.rope_delta, P.n_left_pad, true, false, true);
-        for (int k = tid; k < Ht; k += NCT) s.hid[k] = s.xs[k];   // past_hidden = post-norm hidden (generate.py:198)
+        for (int k = tid; k < Ht; k += NCT) s.hid[k] = xs_get<BF>(c, k);   // past_hidden = post-norm hidden (generate.py:198)
         csync();
         head_logits<BF>(c, P.t.seg_head, Ht);
         SampleArgs sa;

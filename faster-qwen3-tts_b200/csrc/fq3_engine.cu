@@ -41,7 +41,7 @@ struct SegHost {
 struct PackGrp {
   uint64_t tape_off;
   uint32_t rowsrc_idx;
-  uint16_t rows, m, ntiles, pad;
+  uint16_t rows, m, ntiles, pad;   // fp32 layout: rows, 512-byte chunks per tile; mma layout: n_mt | kind << 8, G
   int32_t K;
 };
 
@@ -108,6 +108,45 @@ __global__ void pack_kernel(const PackGrp* __restrict__ pg, int npg, const void*
         v = *reinterpret_cast<const uint4*>(src + ((size_t)kb * 128 + lane * 4) * 4);
       }
       dst[q] = v;
+    }
+  }
+}
+
+// bf16 tensor-core layout: per tile [m-tile][k-group][step 0..3][lane][16 B] holding mma.m16n8k16 A fragments
+// (a0,a1,a2,a3) = rowA[kk,kk+1], rowB[kkB,kkB+1], rowA[kk+2,kk+3], rowB[kkB+2,kkB+3], kk = 64*kgroup + 16*t + 4*step.
+// kind 0 FULL: rowA = r0+16*mt+g, rowB = rowA+8;  kind 1 HALF: rowA = rowB = r0+g, kkB = K/2 + kk;
+// kind 2 GU: rowA = gate row, rowB = up row of pair r0/2 + 8*mt + g (rowsrc holds gate/up interleaved).
+__global__ void pack_mma_kernel(const PackGrp* __restrict__ pg, int npg, const void* const* __restrict__ rowsrc,
+                                uint8_t* __restrict__ tape) {
+  for (int b = blockIdx.x; b < npg; b += gridDim.x) {
+    const PackGrp g = pg[b];
+    const int n_mt = g.rows & 0xff, kind = g.rows >> 8, G = g.m;
+    const long long total = (long long)g.ntiles * n_mt * G * 128;
+    uint4* dst = reinterpret_cast<uint4*>(tape + g.tape_off);
+    for (long long q = threadIdx.x; q < total; q += blockDim.x) {
+      const int lane = (int)(q & 31), st = (int)((q >> 5) & 3);
+      long long rem = q >> 7;
+      const int qq = (int)(rem % G);
+      rem /= G;
+      const int mt = (int)(rem % n_mt);
+      const int tl = (int)(rem / n_mt);
+      const int gq = lane >> 2, t = lane & 3;
+      const int kk = 64 * (tl * G + qq) + 16 * t + 4 * st;
+      const uint8_t *ra, *rb;
+      int kb = kk;
+      if (kind == 0) {
+        ra = reinterpret_cast<const uint8_t*>(rowsrc[g.rowsrc_idx + mt * 16 + gq]);
+        rb = reinterpret_cast<const uint8_t*>(rowsrc[g.rowsrc_idx + mt * 16 + gq + 8]);
+      } else if (kind == 1) {
+        ra = rb = reinterpret_cast<const uint8_t*>(rowsrc[g.rowsrc_idx + gq]);
+        kb = g.K / 2 + kk;
+      } else {
+        ra = reinterpret_cast<const uint8_t*>(rowsrc[g.rowsrc_idx + 2 * (mt * 8 + gq)]);
+        rb = reinterpret_cast<const uint8_t*>(rowsrc[g.rowsrc_idx + 2 * (mt * 8 + gq) + 1]);
+      }
+      const uint2 a = *reinterpret_cast<const uint2*>(ra + (size_t)kk * 2);
+      const uint2 c = *reinterpret_cast<const uint2*>(rb + (size_t)kb * 2);
+      dst[q] = make_uint4(a.x, c.x, a.y, c.y);
     }
   }
 }
@@ -256,6 +295,7 @@ extern "C" int fq3_engine_create(const fq3_config* cfg, fq3_engine** out) {
   k.has_mtp = cfg->has_mtp_projection; k.ncb = cfg->num_code_groups - 1; k.eos = cfg->codec_eos_token_id;
   k.max_seq_len = cfg->max_seq_len;
   k.dbg = e->dbg; k.dbg_stride_layer = e->dbg_stride;
+  k.pred_pin_layers = 2;
   k.sp_t = Sampling{1, 50, 0.9f, 1.0f, 1.05f};
   k.sp_p = Sampling{1, 50, 0.9f, 1.0f, 1.0f};
   *out = e;
@@ -420,11 +460,65 @@ extern "C" int fq3_engine_load_weights(fq3_engine* e, const fq3_tensor* tensors,
   std::vector<uint32_t> segtab((size_t)ncta * nseg, 0);
   std::vector<PackGrp> pack;
   // per-CTA byte totals to place groups: first pass collects sizes
-  struct Tmp { int cta, seg, row0, rows, m, ntiles; uint64_t bytes; };
+  struct Tmp { int cta, seg, row0, rows, m, ntiles; uint64_t bytes; uint32_t rsrc; };
   std::vector<Tmp> tmp;
   int rot = 0;
+  // which segments are gate/up (interleaved) segments
+  std::vector<char> seg_is_gu(nseg, 0);
+  for (int si = 0; si < 2; ++si)
+    for (int l = 0; l < sn[si].c->num_hidden_layers; ++l) seg_is_gu[sn[si].s->seg_base + 4 * l + 2] = 1;
   for (int sg = 0; sg < nseg; ++sg) {
     const int rows = segs[sg].rows, K = segs[sg].K;
+    segs[sg].bytes = (uint64_t)rows * K * esz;
+    if (e->bf16) {
+      // ---- tensor-core layout: units of 8 rows (plain) or 8 gate/up pairs (GU)
+      const bool gu = seg_is_gu[sg];
+      const int unit_rows = gu ? 16 : 8;
+      if (rows % unit_rows || K % 128) return fail(FQ3_ERR_INVALID, "segment %d: rows %d / K %d not tileable for the bf16 tensor-core tape", sg, rows, K);
+      const int units = rows / unit_rows, base = units / ncta, extra = units % ncta;
+      int unit0 = 0;
+      for (int c = 0; c < ncta; ++c) {
+        const int uc = base + ((((c - rot) % ncta + ncta) % ncta) < extra ? 1 : 0);
+        const int begin = (int)cta_grps[c].size();
+        int ng = 0;
+        auto emit = [&](int kind, int n_mt, int row0, uint32_t rsrc) {
+          const int Keff = kind == 1 ? K / 2 : K;
+          const int KG = Keff / 64;
+          int G = 1;
+          for (int d = 1; d <= KG; ++d)
+            if (KG % d == 0 && n_mt * d <= 16) G = d;
+          Tmp t{c, sg, row0, n_mt | (kind << 8), G, KG / G, (uint64_t)n_mt * KG * 2048, rsrc};
+          tmp.push_back(t);
+          Grp g; g.off16 = 0; g.row0 = row0; g.rows = (uint16_t)(n_mt | (kind << 8)); g.m = (uint16_t)G;
+          g.ntiles = (uint16_t)(KG / G); g.pad = 0;
+          cta_grps[c].push_back(g);
+          ++ng;
+        };
+        if (gu) {
+          for (int u = 0; u < uc; u += 2) {
+            const int n_mt = std::min(2, uc - u);
+            const int pair0 = (unit0 + u) * 8;
+            emit(2, n_mt, pair0, seg_rowsrc0[sg] + 2u * pair0);
+          }
+        } else {
+          const int nfull = uc / 2;
+          for (int f = 0; f < nfull; f += 2) {
+            const int n_mt = std::min(2, nfull - f);
+            const int r0 = (unit0 + 2 * f) * 8;
+            emit(0, n_mt, r0, seg_rowsrc0[sg] + (uint32_t)r0);
+          }
+          if (uc % 2) {
+            const int r0 = (unit0 + uc - 1) * 8;
+            emit(1, 1, r0, seg_rowsrc0[sg] + (uint32_t)r0);
+          }
+        }
+        if (ng > 255) return fail(FQ3_ERR_INVALID, "segment %d: too many groups per CTA", sg);
+        segtab[(size_t)c * nseg + sg] = ((uint32_t)begin << 8) | (uint32_t)ng;
+        unit0 += uc;
+      }
+      rot = (rot + extra) % ncta;
+      continue;
+    }
     if (rows % 2 || K % EPW) return fail(FQ3_ERR_INVALID, "segment %d: rows %d must be even and K %d a multiple of %d", sg, rows, K, EPW);
     const int KB = K / EPW;
     const int pairs = rows / 2, base = pairs / ncta, extra = pairs % ncta;
@@ -442,7 +536,7 @@ extern "C" int fq3_engine_load_weights(fq3_engine* e, const fq3_tensor* tensors,
         for (int d = 1; d <= KB; ++d)
           if (KB % d == 0 && (size_t)gr * 512 * d <= (size_t)STAGE_BYTES) m = d;
         const int ntiles = KB / m;
-        Tmp t{c, sg, r0, gr, m, ntiles, (uint64_t)gr * K * esz};
+        Tmp t{c, sg, r0, gr, m, ntiles, (uint64_t)gr * K * esz, seg_rowsrc0[sg] + (uint32_t)r0};
         tmp.push_back(t);
         Grp g; g.off16 = 0; g.row0 = r0; g.rows = (uint16_t)gr; g.m = (uint16_t)m; g.ntiles = (uint16_t)ntiles; g.pad = 0;
         cta_grps[c].push_back(g);
@@ -453,7 +547,6 @@ extern "C" int fq3_engine_load_weights(fq3_engine* e, const fq3_tensor* tensors,
       row += rows_c;
     }
     rot = (rot + extra) % ncta;
-    segs[sg].bytes = (uint64_t)rows * K * esz;
   }
   // tape offsets: CTA-major, segment order
   std::vector<uint64_t> cta_base(ncta + 1, 0);
@@ -470,7 +563,7 @@ extern "C" int fq3_engine_load_weights(fq3_engine* e, const fq3_tensor* tensors,
     for (auto& t : tmp) {
       Grp& g = cta_grps[t.cta][gidx[t.cta]++];
       g.off16 = (uint32_t)(cur[t.cta] / 16);
-      PackGrp pg; pg.tape_off = cur[t.cta]; pg.rowsrc_idx = seg_rowsrc0[t.seg] + (uint32_t)t.row0;
+      PackGrp pg; pg.tape_off = cur[t.cta]; pg.rowsrc_idx = t.rsrc;
       pg.rows = (uint16_t)t.rows; pg.m = (uint16_t)t.m; pg.ntiles = (uint16_t)t.ntiles; pg.pad = 0; pg.K = segs[t.seg].K;
       pack.push_back(pg);
       cur[t.cta] += t.bytes;
@@ -504,7 +597,7 @@ extern "C" int fq3_engine_load_weights(fq3_engine* e, const fq3_tensor* tensors,
   CK(cudaMemcpyAsync(d_pack, pack.data(), pack.size() * sizeof(PackGrp), cudaMemcpyHostToDevice, stream));
   {
     const int grid = (int)std::min<size_t>(pack.size(), 148 * 16);
-    if (e->bf16) pack_kernel<true><<<grid, 256, 0, stream>>>(d_pack, (int)pack.size(), (const void* const*)d_rowsrc, e->tape);
+    if (e->bf16) pack_mma_kernel<<<grid, 256, 0, stream>>>(d_pack, (int)pack.size(), (const void* const*)d_rowsrc, e->tape);
     else pack_kernel<false><<<grid, 256, 0, stream>>>(d_pack, (int)pack.size(), (const void* const*)d_rowsrc, e->tape);
     e->launches++;
     CK(cudaGetLastError());
@@ -512,6 +605,7 @@ extern "C" int fq3_engine_load_weights(fq3_engine* e, const fq3_tensor* tensors,
   CK(cudaStreamSynchronize(stream));
   cudaFree(d_rowsrc);
   cudaFree(d_pack);
+  k.mma_tape = e->bf16 ? 1 : 0;
   k.tape = e->tape; k.grps = e->grps; k.segtab = e->segtab; k.cta_grp_off = e->cta_grp_off;
   // ---- byte accounting (algorithmic bytes)
   {
