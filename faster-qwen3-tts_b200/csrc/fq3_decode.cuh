@@ -266,6 +266,39 @@ __device__ __forceinline__ void grid_sync_v2(Ctx& c) {  // two-level: 16 group c
   csync();
 }
 
+__device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void grid_sync_v3(Ctx& c) {  // relaxed polling, a single acquire fence at the end
+  csync();
+  if (c.tid == 0) {
+    c.bar_target += (unsigned)c.P.ncta;
+    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(c.P.bar), "r"(1u) : "memory");
+    while (ld_relaxed_u32(c.P.bar) < c.bar_target) {
+    }
+    asm volatile("fence.acq_rel.gpu;" ::: "memory");
+  }
+  csync();
+}
+__device__ __forceinline__ void grid_sync_v4(Ctx& c) {  // last arriver writes one flag per CTA (128 B apart)
+  csync();
+  if (c.tid == 0) {
+    c.bar_target += 1;  // epoch
+    unsigned old;
+    asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], %2;" : "=r"(old) : "l"(c.P.bar), "r"(1u) : "memory");
+    unsigned* flags = c.P.bar + 32;
+    if (old + 1 == (unsigned)c.P.ncta * c.bar_target) {
+      for (int i = 0; i < c.P.ncta; ++i)
+        asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(flags + 32 * i), "r"(c.bar_target) : "memory");
+    }
+    while (ld_acquire_u32(flags + 32 * blockIdx.x) < c.bar_target) {
+    }
+  }
+  csync();
+}
+
 __device__ __forceinline__ float block_sum(Ctx& c, float v) {
 #pragma unroll
   for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -548,7 +581,7 @@ __device__ void attention_head(Ctx& c, const StackDev& S, int layer, int h, int 
       constexpr int LPK = BF ? 16 : 32;  // lanes per key (16 bytes per lane)
       constexpr int KPW = 32 / LPK;      // keys per warp-instruction
       constexpr int EPL = BF ? 8 : 4;
-      constexpr int U = 8;
+      constexpr int U = 16;
       const int sub = c.lane % LPK, kin = c.lane / LPK;
       float q[EPL];
 #pragma unroll
@@ -612,7 +645,7 @@ __device__ void attention_head(Ctx& c, const StackDev& S, int layer, int h, int 
       constexpr int LPK = BF ? 16 : 32;
       constexpr int KPW = 32 / LPK;
       constexpr int EPL = BF ? 8 : 4;
-      constexpr int U = 8;
+      constexpr int U = 16;
       const int sub = c.lane % LPK, kin = c.lane / LPK;
       float acc[EPL];
 #pragma unroll
@@ -1038,47 +1071,66 @@ __device__ __forceinline__ float xs_get(Ctx& c, int idx) {
 // This removes the attention exchange (ATT round trip) and one grid barrier per layer.  One warp per kv group;
 // a lane owns dims [4*lane, 4*lane+4) of every 128-vector; CTA 0 appends the new K/V to the cache.
 // ------------------------------------------------------------------------------------------------------------
-template <bool BF>
-__device__ void attention_small_all(Ctx& c, const StackDev& S, int layer, int nt, int slot0, int rpos0) {
+// NT == 2 is the predictor prefill (slot0 == 0: no cached keys at all); NT == 1 the single-token passes.
+// Register budget is 168/thread (9 warps per SM), so K rows and V rows are fetched in two round trips.
+template <bool BF, int NT>
+__device__ void attention_small_all(Ctx& c, const StackDev& S, int layer, int slot0_, int rpos0) {
   const KParams& P = c.P;
-  constexpr int MAXK = 18;
+  constexpr int NOLD = NT == 2 ? 1 : 16;  // cached keys that can exist
+  constexpr int MAXK = NT == 2 ? 2 : 17;
+  const int slot0 = NT == 2 ? 0 : slot0_;
   const float scale = 0.08838834764831845f;
   const size_t esz = BF ? 2 : 4;
   const int L4 = 4 * c.lane;
+  using Raw = typename std::conditional<BF, uint2, float4>::type;
+  auto unpack = [](const Raw& r, float* o) {
+    if constexpr (BF) { o[0] = bf_lo(r.x); o[1] = bf_hi(r.x); o[2] = bf_lo(r.y); o[3] = bf_hi(r.y); }
+    else { o[0] = r.x; o[1] = r.y; o[2] = r.z; o[3] = r.w; }
+  };
+  auto zero_raw = [](Raw& r) {
+    if constexpr (BF) r = make_uint2(0, 0);
+    else r = make_float4(0, 0, 0, 0);
+  };
   for (int g = c.warp; g < S.nKV; g += NCW) {
     const uint8_t* kb = reinterpret_cast<const uint8_t*>(S.kc) + ((size_t)(layer * S.nKV + g) * S.S * 128) * esz;
     const uint8_t* vb = reinterpret_cast<const uint8_t*>(S.vc) + ((size_t)(layer * S.nKV + g) * S.S * 128) * esz;
-    // ---- issue every global load up front: old K/V rows (kept packed: 16 bytes fp32 / 8 bytes bf16 per lane)
-    using Raw = typename std::conditional<BF, uint2, float4>::type;
-    Raw kraw[16], vraw[16];
+    // ---- round trip 1: cached K rows + everything about the new token(s)
+    Raw kraw[NOLD];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      if (j < slot0) {
-        kraw[j] = __ldcg(reinterpret_cast<const Raw*>(kb + (size_t)j * 128 * esz) + c.lane);
-        vraw[j] = __ldcg(reinterpret_cast<const Raw*>(vb + (size_t)j * 128 * esz) + c.lane);
-      } else {
-        if constexpr (BF) { kraw[j] = make_uint2(0, 0); vraw[j] = make_uint2(0, 0); }
-        else { kraw[j] = make_float4(0, 0, 0, 0); vraw[j] = make_float4(0, 0, 0, 0); }
+    for (int j = 0; j < NOLD; ++j) {
+      if (j < slot0) kraw[j] = __ldcg(reinterpret_cast<const Raw*>(kb + (size_t)j * 128 * esz) + c.lane);
+      else zero_raw(kraw[j]);
+    }
+    float4 qn4, kn4, cs4[NT], sn4[NT], kr4[NT], vr4[NT], qr4[2][NT];
+    {
+      float qn[4], kn[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        qn[i] = ldw<BF>(S.qnorm, (size_t)layer * 128 + L4 + i);
+        kn[i] = ldw<BF>(S.knorm, (size_t)layer * 128 + L4 + i);
       }
+      qn4 = make_float4(qn[0], qn[1], qn[2], qn[3]);
+      kn4 = make_float4(kn[0], kn[1], kn[2], kn[3]);
     }
-    auto unpack = [](const Raw& r, float* o) {
-      if constexpr (BF) { o[0] = bf_lo(r.x); o[1] = bf_hi(r.x); o[2] = bf_lo(r.y); o[3] = bf_hi(r.y); }
-      else { o[0] = r.x; o[1] = r.y; o[2] = r.z; o[3] = r.w; }
-    };
-    float qn[4], kn[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      qn[i] = ldw<BF>(S.qnorm, (size_t)layer * 128 + L4 + i);
-      kn[i] = ldw<BF>(S.knorm, (size_t)layer * 128 + L4 + i);
+    for (int t = 0; t < NT; ++t) {
+      int rp = rpos0 + t;
+      rp = rp < 0 ? 0 : (rp >= S.npos ? S.npos - 1 : rp);
+      cs4[t] = __ldg(reinterpret_cast<const float4*>(S.cos + (size_t)rp * 128) + c.lane);
+      sn4[t] = __ldg(reinterpret_cast<const float4*>(S.sin + (size_t)rp * 128) + c.lane);
+      const size_t tb = (size_t)t * P.ldQKV;
+      kr4[t] = __ldcg(reinterpret_cast<const float4*>(P.QKV + tb + S.qd + g * 128) + c.lane);
+      vr4[t] = __ldcg(reinterpret_cast<const float4*>(P.QKV + tb + S.qd + S.kd + g * 128) + c.lane);
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh)
+        qr4[hh][t] = __ldcg(reinterpret_cast<const float4*>(P.QKV + tb + (g * S.rep + (hh < S.rep ? hh : 0)) * 128) + c.lane);
     }
-    float knew[2][4], vnew[2][4];
-    // rms-norm + rope of one 128-vector held as 4 dims per lane (pairs d, d+64 live in lanes l, l^16)
-    auto norm_rope = [&](float* v, const float* w, int rp) {
+    auto norm_rope = [&](float* v, const float4& w4, const float4& c4, const float4& s4) {
+      const float w[4] = {w4.x, w4.y, w4.z, w4.w}, cc[4] = {c4.x, c4.y, c4.z, c4.w}, sv[4] = {s4.x, s4.y, s4.z, s4.w};
       float ss = v[0] * v[0] + v[1] * v[1] + v[2] * v[2] + v[3] * v[3];
 #pragma unroll
       for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
       const float r = 1.0f / sqrtf(ss / 128.0f + S.eps);
-      rp = rp < 0 ? 0 : (rp >= S.npos ? S.npos - 1 : rp);
       float o4[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) v[i] = rnd<BF>(w[i] * rnd<BF>(v[i] * r));
@@ -1086,20 +1138,17 @@ __device__ void attention_small_all(Ctx& c, const StackDev& S, int layer, int nt
       for (int i = 0; i < 4; ++i) {
         const float other = __shfl_xor_sync(0xffffffffu, v[i], 16);
         const float rot = c.lane < 16 ? -other : other;
-        const float cc = rnd<BF>(__ldg(S.cos + (size_t)rp * 128 + L4 + i)), sv = rnd<BF>(__ldg(S.sin + (size_t)rp * 128 + L4 + i));
-        o4[i] = rnd<BF>(rnd<BF>(v[i] * cc) + rnd<BF>(rot * sv));
+        o4[i] = rnd<BF>(rnd<BF>(v[i] * rnd<BF>(cc[i])) + rnd<BF>(rot * rnd<BF>(sv[i])));
       }
 #pragma unroll
       for (int i = 0; i < 4; ++i) v[i] = o4[i];
     };
+    float knew[NT][4], vnew[NT][4];
 #pragma unroll
-    for (int t = 0; t < 2; ++t) {
-      if (t < nt) {
-      const float4 kr = __ldcg(reinterpret_cast<const float4*>(P.QKV + (size_t)t * P.ldQKV + S.qd + g * 128) + c.lane);
-      const float4 vr = __ldcg(reinterpret_cast<const float4*>(P.QKV + (size_t)t * P.ldQKV + S.qd + S.kd + g * 128) + c.lane);
-      knew[t][0] = kr.x; knew[t][1] = kr.y; knew[t][2] = kr.z; knew[t][3] = kr.w;
-      vnew[t][0] = vr.x; vnew[t][1] = vr.y; vnew[t][2] = vr.z; vnew[t][3] = vr.w;
-      norm_rope(knew[t], kn, rpos0 + t);
+    for (int t = 0; t < NT; ++t) {
+      knew[t][0] = kr4[t].x; knew[t][1] = kr4[t].y; knew[t][2] = kr4[t].z; knew[t][3] = kr4[t].w;
+      vnew[t][0] = vr4[t].x; vnew[t][1] = vr4[t].y; vnew[t][2] = vr4[t].z; vnew[t][3] = vr4[t].w;
+      norm_rope(knew[t], kn4, cs4[t], sn4[t]);
       if (blockIdx.x == 0) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -1107,70 +1156,103 @@ __device__ void attention_small_all(Ctx& c, const StackDev& S, int layer, int nt
           stw<BF>(const_cast<uint8_t*>(vb) + (size_t)(slot0 + t) * 128 * esz, L4 + i, vnew[t][i]);
         }
       }
-      } else {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) { knew[t][i] = 0.f; vnew[t][i] = 0.f; }
-      }
     }
-    for (int hh = 0; hh < S.rep; ++hh) {
-      const int h = g * S.rep + hh;
+    // ---- scores of every (head, token) of this group; probabilities stay in registers
+    float q[2][NT][4];
 #pragma unroll
-      for (int t = 0; t < 2; ++t) {
-        if (t < nt) {
-        const float4 qr = __ldcg(reinterpret_cast<const float4*>(P.QKV + (size_t)t * P.ldQKV + h * 128) + c.lane);
-        float q[4] = {qr.x, qr.y, qr.z, qr.w};
-        norm_rope(q, qn, rpos0 + t);
-        const int nk = slot0 + t + 1;  // visible keys: cache slots [0, slot0) then new tokens 0..t
-        float sc[MAXK];
+    for (int hh = 0; hh < 2; ++hh)
 #pragma unroll
-        for (int j = 0; j < MAXK; ++j) {
-          float d = 0.f;
-          if (j < 16) {
-            float kf[4];
-            unpack(kraw[j], kf);
-            d = q[0] * kf[0];
-            d = fmaf(q[1], kf[1], d); d = fmaf(q[2], kf[2], d); d = fmaf(q[3], kf[3], d);
-          }
-          // new keys occupy positions slot0 .. slot0+t
-          if (j == slot0) { d = q[0] * knew[0][0]; d = fmaf(q[1], knew[0][1], d); d = fmaf(q[2], knew[0][2], d); d = fmaf(q[3], knew[0][3], d); }
-          if (nt == 2 && j == slot0 + 1) { d = q[0] * knew[1][0]; d = fmaf(q[1], knew[1][1], d); d = fmaf(q[2], knew[1][2], d); d = fmaf(q[3], knew[1][3], d); }
+      for (int t = 0; t < NT; ++t) {
+        q[hh][t][0] = qr4[hh][t].x; q[hh][t][1] = qr4[hh][t].y; q[hh][t][2] = qr4[hh][t].z; q[hh][t][3] = qr4[hh][t].w;
+        norm_rope(q[hh][t], qn4, cs4[t], sn4[t]);
+      }
+    float sc[2][NT][MAXK];
 #pragma unroll
-          for (int o = 16; o; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
-          sc[j] = j < nk ? rnd<BF>(rnd<BF>(d) * scale) : -INFINITY;
+    for (int j = 0; j < MAXK; ++j) {
+      float kf[4] = {0.f, 0.f, 0.f, 0.f};
+      if (j < NOLD && j < slot0) unpack(kraw[j < NOLD ? j : 0], kf);
+#pragma unroll
+      for (int tn = 0; tn < NT; ++tn)
+        if (j == slot0 + tn) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) kf[i] = knew[tn][i];
         }
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh)
+#pragma unroll
+        for (int t = 0; t < NT; ++t) {
+          float d = q[hh][t][0] * kf[0];
+          d = fmaf(q[hh][t][1], kf[1], d); d = fmaf(q[hh][t][2], kf[2], d); d = fmaf(q[hh][t][3], kf[3], d);
+          sc[hh][t][j] = d;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1)
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh)
+#pragma unroll
+        for (int t = 0; t < NT; ++t)
+#pragma unroll
+          for (int j = 0; j < MAXK; ++j) sc[hh][t][j] += __shfl_xor_sync(0xffffffffu, sc[hh][t][j], o);
+    // ---- round trip 2: cached V rows (issued before the softmax arithmetic so the latency overlaps it)
+    Raw vraw[NOLD];
+#pragma unroll
+    for (int j = 0; j < NOLD; ++j) {
+      if (j < slot0) vraw[j] = __ldcg(reinterpret_cast<const Raw*>(vb + (size_t)j * 128 * esz) + c.lane);
+      else zero_raw(vraw[j]);
+    }
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh)
+#pragma unroll
+      for (int t = 0; t < NT; ++t) {
+        const int nk = slot0 + t + 1;
         float mx = -INFINITY;
 #pragma unroll
-        for (int j = 0; j < MAXK; ++j) mx = fmaxf(mx, sc[j]);
+        for (int j = 0; j < MAXK; ++j) {
+          sc[hh][t][j] = j < nk ? rnd<BF>(rnd<BF>(sc[hh][t][j]) * scale) : -INFINITY;
+          mx = fmaxf(mx, sc[hh][t][j]);
+        }
         float sm = 0.f;
 #pragma unroll
         for (int j = 0; j < MAXK; ++j) {
-          sc[j] = j < nk ? expf(sc[j] - mx) : 0.f;
-          sm += sc[j];
-        }
-        float o4[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-        for (int j = 0; j < MAXK; ++j) {
-          const float pj = rnd<BF>(sc[j] / sm);
-          if (j < 16) {
-            float vf[4];
-            unpack(vraw[j], vf);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) o4[i] = fmaf(pj, j < slot0 ? vf[i] : 0.f, o4[i]);
-          }
-          if (j == slot0) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) o4[i] = fmaf(pj, vnew[0][i], o4[i]);
-          }
-          if (nt == 2 && j == slot0 + 1) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) o4[i] = fmaf(pj, vnew[1][i], o4[i]);
-          }
+          sc[hh][t][j] = j < nk ? (BF ? __expf(sc[hh][t][j] - mx) : expf(sc[hh][t][j] - mx)) : 0.f;
+          sm += sc[hh][t][j];
         }
 #pragma unroll
-        for (int i = 0; i < 4; ++i) xs_put<BF>(c, t * S.qd + h * 128 + L4 + i, rnd<BF>(o4[i]));
-        }
+        for (int j = 0; j < MAXK; ++j) sc[hh][t][j] = rnd<BF>(BF ? __fdividef(sc[hh][t][j], sm) : sc[hh][t][j] / sm);
       }
+    float o4[2][NT][4];
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh)
+#pragma unroll
+      for (int t = 0; t < NT; ++t)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) o4[hh][t][i] = 0.f;
+#pragma unroll
+    for (int j = 0; j < MAXK; ++j) {
+      float vf[4] = {0.f, 0.f, 0.f, 0.f};
+      if (j < NOLD && j < slot0) unpack(vraw[j < NOLD ? j : 0], vf);
+#pragma unroll
+      for (int tn = 0; tn < NT; ++tn)
+        if (j == slot0 + tn) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) vf[i] = vnew[tn][i];
+        }
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh)
+#pragma unroll
+        for (int t = 0; t < NT; ++t)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) o4[hh][t][i] = fmaf(sc[hh][t][j], vf[i], o4[hh][t][i]);
     }
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh)
+      if (hh < S.rep)
+#pragma unroll
+        for (int t = 0; t < NT; ++t)
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            xs_put<BF>(c, t * S.qd + (g * S.rep + hh) * 128 + L4 + i, rnd<BF>(o4[hh][t][i]));
   }
   csync();
 }
@@ -1235,10 +1317,11 @@ __device__ void run_layers(Ctx& c, const StackDev& S, int nt, int slot0, int rpo
       for (int t = 0; t < nt; ++t)
         for (int k = c.tid; k < S.qd + 2 * S.kd; k += NCT) d[(size_t)t * (S.qd + 2 * S.kd) + k] = __ldcg(P.QKV + (size_t)t * P.ldQKV + k);
     }
-    const bool small_attn = !is_talker && S.S <= 32 && slot0 + nt <= 17;
+    const bool small_attn = !is_talker && S.S <= 32 && S.rep <= 2 && ((nt == 1 && slot0 <= 16) || (nt == 2 && slot0 == 0));
     if (small_attn) {
       // ---- P2+P3 fused: redundant small attention straight into the staging vector (no exchange, no barrier)
-      attention_small_all<BF>(c, S, l, nt, slot0, rpos0);
+      if (nt == 1) attention_small_all<BF, 1>(c, S, l, slot0, rpos0);
+      else attention_small_all<BF, 2>(c, S, l, slot0, rpos0);
       probe(c, pi);  // 4
       probe(c, pi);  // 5
     } else {
@@ -1439,7 +1522,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) fq3_decode_kernel(const __grid_co
       for (int i = 0; i < P.n_frames; ++i) {
         if (P.position == 0) grid_sync_v0(c);
         else if (P.position == 1) grid_sync_v1(c);
-        else grid_sync_v2(c);
+        else if (P.position == 2) grid_sync_v2(c);
+        else if (P.position == 3) grid_sync_v3(c);
+        else grid_sync_v4(c);
       }
     } else if (P.mode == MODE_TALKER_STEP) {
       for (int k = tid; k < Ht; k += NCT) s.xin[0][k] = ldw<BF>(P.in_embeds, k);

@@ -265,7 +265,7 @@ extern "C" int fq3_engine_create(const fq3_config* cfg, fq3_engine** out) {
   CK(cudaMalloc(&e->X, 2 * ldX * sizeof(float))); CK(cudaMalloc(&e->X1, 2 * ldX * sizeof(float)));
   CK(cudaMalloc(&e->QKV, 2 * ldQKV * sizeof(float))); CK(cudaMalloc(&e->ATT, 2 * ldATT * sizeof(float)));
   CK(cudaMalloc(&e->ACT, 2 * ldACT * sizeof(float))); CK(cudaMalloc(&e->LOGITS, VMAX * sizeof(float)));
-  CK(cudaMalloc(&e->bar, 4096)); CK(cudaMemset(e->bar, 0, 4096));
+  CK(cudaMalloc(&e->bar, 32768)); CK(cudaMemset(e->bar, 0, 32768));
   CK(cudaMalloc(&e->state, 64)); CK(cudaMemset(e->state, 0, 64));
   CK(cudaMallocHost(&e->state_host, 64));
   CK(cudaMalloc(&e->past_hidden, HMAX * sizeof(float))); CK(cudaMemset(e->past_hidden, 0, HMAX * sizeof(float)));
@@ -626,7 +626,7 @@ extern "C" int fq3_engine_load_weights(fq3_engine* e, const fq3_tensor* tensors,
 // launches
 // ------------------------------------------------------------------------------------------------------------
 static int launch_decode(fq3_engine* e, const KParams& kp, cudaStream_t stream) {
-  CK(cudaMemsetAsync(e->bar, 0, 4096, stream));
+  CK(cudaMemsetAsync(e->bar, 0, 32768, stream));
   void* args[] = {(void*)&kp};
   if (e->bf16)
     CK(cudaLaunchCooperativeKernel((const void*)fq3_decode_kernel<true>, dim3(e->ncta), dim3(NTHREADS), args, smem_bytes(), stream));

@@ -33,7 +33,7 @@ for ds in (False, True):
     ms = timeit(lambda: eng.predictor_run(pi, SamplingParams(do_sample=ds), u))
     print(json.dumps({"what": "predictor_run", "do_sample": ds, "ms": ms, "GBps": pb / ms / 1e6}))
 if hasattr(eng, "barrier_test"):
-    for kind in (0, 1, 2):
+    for kind in (0, 1, 2, 3, 4):
         ms = timeit(lambda: eng.barrier_test(1000, kind), n=5)
         print(json.dumps({"what": "barrier", "kind": kind, "us_per_barrier": ms}))
 
