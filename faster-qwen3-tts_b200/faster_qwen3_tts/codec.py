@@ -209,25 +209,152 @@ class Code2Wav(nn.Module):
 
 
 class SpeechTokenizer:
-    """The decode side of the upstream speech tokenizer, as the reference consumes it."""
+    """The decode side of the upstream speech tokenizer, as the reference consumes it
+    (``decode({"audio_codes": [B,T,16]}) -> ([wav], sample_rate)``).
 
-    def __init__(self, decoder: Code2Wav):
+    backend="engine": the waveform stack (conv_in, 4 upsampling blocks, conv_out: 94% of the decoder FLOPs) runs in
+    the hand-written sm_100a kernels of csrc/fq3_codec.cu through the C ABI; the light front end (code embedding,
+    8-layer pre-transformer, 2 x (ConvTranspose k=2 + ConvNeXt)) stays in torch, captured once per window length in a
+    CUDA graph.  backend="torch": the plain library implementation (functional baseline)."""
+
+    def __init__(self, decoder: Code2Wav, backend: str = "torch", graph_front: bool = True):
         self.decoder = decoder
         self.sample_rate = decoder.config.sample_rate
         self.launches = 0
+        self.backend = backend
+        self.graph_front = graph_front
+        self._h = None
+        self._graphs = {}
+        if backend == "engine":
+            self._init_engine()
+
+    # ---- engine plumbing -------------------------------------------------------------------------------
+    def _init_engine(self):
+        import ctypes as C
+        from .engine import Tensor, load_library
+        lib = load_library()
+        d = self.decoder
+        c = d.config
+        p0 = next(d.parameters())
+        if p0.device.type != "cuda":
+            raise RuntimeError("codec engine backend needs the decoder on a CUDA device")
+        self._lib, self._dev = lib, p0.device
+        geom = [p0.device.index or 0, c.hidden_size, c.decoder_dim, len(c.upsample_rates)] + list(c.upsample_rates)
+        arr = (C.c_int32 * len(geom))(*geom)
+        h = C.c_void_p()
+        if lib.fq3_codec_create(arr, len(geom), C.byref(h)):
+            raise RuntimeError(lib.fq3_codec_last_error().decode())
+        t = {}
+
+        def put(name, x):
+            t[name] = x.detach().to(torch.float32).contiguous()
+
+        put("conv_in.w", d.conv_in.conv.weight); put("conv_in.b", d.conv_in.conv.bias)
+        for i, b in enumerate(d.blocks):
+            put(f"b{i}.act.a", b.act.alpha); put(f"b{i}.act.b", b.act.beta)
+            put(f"b{i}.up.w", b.up.conv.weight); put(f"b{i}.up.b", b.up.conv.bias)
+            for j, r in enumerate(b.res):
+                q = f"b{i}.r{j}"
+                put(q + ".a1.a", r.act1.alpha); put(q + ".a1.b", r.act1.beta)
+                put(q + ".c1.w", r.conv1.conv.weight); put(q + ".c1.b", r.conv1.conv.bias)
+                put(q + ".a2.a", r.act2.alpha); put(q + ".a2.b", r.act2.beta)
+                put(q + ".c2.w", r.conv2.conv.weight); put(q + ".c2.b", r.conv2.conv.bias)
+        put("out.act.a", d.act_out.alpha); put("out.act.b", d.act_out.beta)
+        put("out.w", d.conv_out.conv.weight); put("out.b", d.conv_out.conv.bias)
+        arr_t = (Tensor * len(t))()
+        for i, (k, v) in enumerate(t.items()):
+            arr_t[i] = Tensor(k.encode(), v.data_ptr(), v.numel())
+        with torch.cuda.device(self._dev):
+            if lib.fq3_codec_load_weights(h, arr_t, len(t), C.c_void_p(torch.cuda.current_stream(self._dev).cuda_stream)):
+                raise RuntimeError(lib.fq3_codec_last_error().decode())
+        self._h = h
+
+    def __del__(self):
+        try:
+            if self._h is not None:
+                self._lib.fq3_codec_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def _front(self, codes: torch.Tensor) -> torch.Tensor:
+        """codes [1,Q,T] -> hidden after the upsampling front end, [1, H, 4T] (model dtype)."""
+        d = self.decoder
+        c = d.config
+        B, Q, T = codes.shape
+        off = (torch.arange(Q, device=codes.device) * c.codebook_size).view(1, Q, 1)
+        x = d.code_embedding(codes + off).mean(1)
+        hd = c.hidden_size // c.num_attention_heads
+        inv = 1.0 / (c.rope_theta ** (torch.arange(0, hd, 2, dtype=torch.float32, device=x.device) / hd))
+        fr = torch.arange(T, dtype=torch.float32, device=x.device)[:, None] * inv[None]
+        emb = torch.cat((fr, fr), dim=-1)
+        cos, sin = emb.cos().to(x.dtype)[None, None], emb.sin().to(x.dtype)[None, None]
+        i = torch.arange(T, device=x.device)
+        allowed = (i[None, :] <= i[:, None]) & (i[None, :] > i[:, None] - c.sliding_window)
+        for l in d.layers:
+            x = l(x, cos, sin, allowed)
+        x = d.norm(x).transpose(1, 2)
+        for up, nx in d.upsample:
+            x = nx(up(x))
+        return x
+
+    def _front_graphed(self, codes: torch.Tensor) -> torch.Tensor:
+        T = codes.shape[-1]
+        g = self._graphs.get(T)
+        if g is None:
+            static_in = codes.clone()
+            s = torch.cuda.Stream(device=codes.device)
+            s.wait_stream(torch.cuda.current_stream(codes.device))
+            with torch.cuda.stream(s):
+                for _ in range(2):
+                    self._front(static_in)
+            torch.cuda.current_stream(codes.device).wait_stream(s)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                static_out = self._front(static_in)
+            g = self._graphs[T] = (graph, static_in, static_out)
+            if len(self._graphs) > 64:
+                self._graphs.pop(next(iter(self._graphs)))
+        graph, static_in, static_out = g
+        static_in.copy_(codes)
+        graph.replay()
+        return static_out
 
     @torch.inference_mode()
     def decode(self, payload) -> Tuple[List[torch.Tensor], int]:
         codes = payload["audio_codes"]  # [B, T, Q]
         dev = next(self.decoder.parameters()).device
-        wav = self.decoder(codes.to(dev).transpose(1, 2))
-        self.launches += 1
-        return [w.reshape(-1).float() for w in wav], self.sample_rate
+        codes = codes.to(dev).transpose(1, 2).contiguous()
+        if self.backend != "engine":
+            wav = self.decoder(codes)
+            self.launches += 1
+            return [w.reshape(-1).float() for w in wav], self.sample_rate
+        import ctypes as C
+        outs = []
+        for b in range(codes.shape[0]):
+            cb = codes[b:b + 1]
+            x = (self._front_graphed(cb) if self.graph_front else self._front(cb))[0].to(torch.bfloat16).contiguous()
+            T4 = x.shape[1]
+            pcm = torch.empty(T4 * (self.decoder.config.total_upsample // 4), dtype=torch.float32, device=dev)
+            with torch.cuda.device(dev):
+                rc = self._lib.fq3_codec_decode(self._h, C.c_void_p(x.data_ptr()), T4, C.c_void_p(pcm.data_ptr()),
+                                                C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+            if rc:
+                raise RuntimeError(self._lib.fq3_codec_last_error().decode())
+            outs.append(pcm)
+        self.launches = int(self._lib.fq3_codec_launch_count(self._h))
+        return outs, self.sample_rate
+
+    def flops(self, T: int) -> float:
+        return float(self._lib.fq3_codec_flops(self._h, 4 * T)) if self._h is not None else 0.0
 
 
-def build_codec(cfg: Code2WavConfig = None, seed: int = 0, dtype=torch.bfloat16, device="cpu") -> SpeechTokenizer:
+def build_codec(cfg: Code2WavConfig = None, seed: int = 0, dtype=torch.bfloat16, device="cpu",
+                backend: str = None) -> SpeechTokenizer:
     cfg = cfg or Code2WavConfig()
     dev = torch.device(device)
+    if backend is None:
+        backend = "engine" if dev.type == "cuda" else "torch"
     with torch.device(dev):
         m = Code2Wav(cfg)
     g = torch.Generator(device=dev).manual_seed(seed)
@@ -247,5 +374,5 @@ def build_codec(cfg: Code2WavConfig = None, seed: int = 0, dtype=torch.bfloat16,
             p.normal_(0.0, 1.0, generator=g)
         else:
             fan_in = p[0].numel()
-            p.normal_(0.0, 1.0 / math.sqrt(fan_in), generator=g)
-    return SpeechTokenizer(m.to(dtype=dtype))
+            p.normal_(0.0, 0.5 / math.sqrt(fan_in), generator=g)
+    return SpeechTokenizer(m.to(dtype=dtype), backend=backend)

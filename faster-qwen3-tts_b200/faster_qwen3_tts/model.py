@@ -152,8 +152,11 @@ class FasterQwen3TTS:
                                   "Use generate_voice_clone() with reference audio.")
 
     def codec_launches(self) -> int:
+        """kernels launched by the hand-written codec stack (bench.py gpu_launches)"""
         st = self._get_speech_tokenizer(self.model)
-        return int(getattr(st, "launches", 0)) if st is not None else 0
+        if st is None or getattr(st, "backend", "torch") != "engine":
+            return 0
+        return int(st._lib.fq3_codec_launch_count(st._h))
 
     # ------------------------------------------------------------------ prompt assembly
     def _is_synthetic(self) -> bool:

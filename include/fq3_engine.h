@@ -164,6 +164,19 @@ int fq3_num_ctas(fq3_engine* e);
 /* number of kernels launched by this engine since creation (bench.py "gpu_launches") */
 int64_t fq3_launch_count(fq3_engine* e);
 
+/* ---- K4: codec waveform decoder stack (replaces the cuDNN path under speech_tokenizer.decode, model.py:924,1093,1122)
+ * geom = {device, hidden_size, decoder_dim, n_blocks, rate_0..rate_{n-1}}.  Tensor names / layouts: csrc/fq3_codec.cu.
+ * fq3_codec_decode: x_dev bf16 [hidden][T4] (channels-first output of the front end) -> pcm float32 [T4*prod(rates)],
+ * clamped to [-1,1]. */
+typedef struct fq3_codec fq3_codec;
+int fq3_codec_create(const int32_t* geom, int32_t n_geom, fq3_codec** out);
+int fq3_codec_load_weights(fq3_codec* c, const fq3_tensor* tensors, int32_t n, void* stream);
+int fq3_codec_decode(fq3_codec* c, const void* x_dev, int32_t T4, float* pcm_out_dev, void* stream);
+double fq3_codec_flops(fq3_codec* c, int32_t T4);
+int64_t fq3_codec_launch_count(fq3_codec* c);
+void fq3_codec_destroy(fq3_codec* c);
+const char* fq3_codec_last_error(void);
+
 const char* fq3_last_error(void);
 const char* fq3_version(void);
 
