@@ -773,7 +773,7 @@ __device__ int sample_block(Ctx& c, const SampleArgs& a) {
   if (a.sp.top_k > 0 && a.sp.top_k < V) {
     uint32_t prefix = 0, mask = 0;
     int remaining = a.sp.top_k;
-    for (int pass = 0; pass < 4; ++pass) {
+    for (int pass = 0; pass < (BF ? 2 : 4); ++pass) {  // bf16-rounded logits have 16 zero low bits
       const int shift = 24 - 8 * pass;
       c.s.hist[c.tid] = 0;
       csync();
@@ -1201,25 +1201,27 @@ __device__ void attention_small_all(Ctx& c, const StackDev& S, int layer, int sl
       if (j < slot0) vraw[j] = __ldcg(reinterpret_cast<const Raw*>(vb + (size_t)j * 128 * esz) + c.lane);
       else zero_raw(vraw[j]);
     }
+    // softmax with the keys distributed over lanes: every lane knows all scores (max is redundant and cheap), but
+    // only lane j exponentiates key j; the sum is a warp reduction and p_j is broadcast with one shuffle per key.
 #pragma unroll
     for (int hh = 0; hh < 2; ++hh)
 #pragma unroll
       for (int t = 0; t < NT; ++t) {
         const int nk = slot0 + t + 1;
-        float mx = -INFINITY;
+        float mx = -INFINITY, mine = -INFINITY;
 #pragma unroll
         for (int j = 0; j < MAXK; ++j) {
-          sc[hh][t][j] = j < nk ? rnd<BF>(rnd<BF>(sc[hh][t][j]) * scale) : -INFINITY;
-          mx = fmaxf(mx, sc[hh][t][j]);
+          const float sj = j < nk ? rnd<BF>(rnd<BF>(sc[hh][t][j]) * scale) : -INFINITY;
+          mx = fmaxf(mx, sj);
+          if (j == c.lane) mine = sj;
         }
-        float sm = 0.f;
+        const float e = (c.lane < nk) ? (BF ? __expf(mine - mx) : expf(mine - mx)) : 0.f;
+        float sm = e;
 #pragma unroll
-        for (int j = 0; j < MAXK; ++j) {
-          sc[hh][t][j] = j < nk ? (BF ? __expf(sc[hh][t][j] - mx) : expf(sc[hh][t][j] - mx)) : 0.f;
-          sm += sc[hh][t][j];
-        }
+        for (int o = 16; o; o >>= 1) sm += __shfl_xor_sync(0xffffffffu, sm, o);
+        const float pmine = rnd<BF>(BF ? __fdividef(e, sm) : e / sm);
 #pragma unroll
-        for (int j = 0; j < MAXK; ++j) sc[hh][t][j] = rnd<BF>(BF ? __fdividef(sc[hh][t][j], sm) : sc[hh][t][j] / sm);
+        for (int j = 0; j < MAXK; ++j) sc[hh][t][j] = __shfl_sync(0xffffffffu, pmine, j);
       }
     float o4[2][NT][4];
 #pragma unroll

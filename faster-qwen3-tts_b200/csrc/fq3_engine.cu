@@ -75,6 +75,10 @@ struct fq3_engine {
   int64_t talker_step_bytes = 0, predictor_frame_bytes = 0;
   KParams kp;  // template parameters (static part)
   int64_t launches = 0;
+  // K3 prefill: borrowed row-major weights + scratch
+  const void *pf_qkv = nullptr, *pf_o = nullptr, *pf_gu = nullptr, *pf_down = nullptr, *pf_head = nullptr;
+  void* pf_buf[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  bool pf_ready = false;
 };
 
 static size_t smem_bytes() { return sizeof(Smem); }
@@ -311,6 +315,8 @@ extern "C" void fq3_engine_destroy(fq3_engine* e) {
     if (p) cudaFree(p);
   for (auto& kv : e->tabs)
     if (kv.second) cudaFree(kv.second);
+  for (void* p : e->pf_buf)
+    if (p) cudaFree(p);
   if (e->state_host) cudaFreeHost(e->state_host);
   delete e;
 }
@@ -805,3 +811,5 @@ extern "C" int fq3_num_ctas(fq3_engine* e) { return e ? e->ncta : 0; }
 extern "C" int64_t fq3_launch_count(fq3_engine* e) { return e ? e->launches : 0; }
 extern "C" const char* fq3_last_error(void) { return g_err; }
 extern "C" const char* fq3_version(void) { return "fq3-b200 0.1.0 (sm_100a)"; }
+
+#include "fq3_prefill.cuh"

@@ -61,7 +61,7 @@ EXPORTS = [
     "fq3_engine_create", "fq3_engine_load_weights", "fq3_engine_destroy", "fq3_import_kv",
     "fq3_set_generation_state", "fq3_talker_step", "fq3_predictor_run", "fq3_sample_logits", "fq3_begin_request",
     "fq3_decode_chunk", "fq3_get_past_hidden", "fq3_debug_enable", "fq3_debug_read", "fq3_tape_bytes",
-    "fq3_num_ctas", "fq3_launch_count", "fq3_last_error", "fq3_version", "fq3_barrier_test",
+    "fq3_num_ctas", "fq3_launch_count", "fq3_last_error", "fq3_version", "fq3_barrier_test", "fq3_engine_set_prefill_weights", "fq3_prefill",
     "fq3_codec_create", "fq3_codec_load_weights", "fq3_codec_decode", "fq3_codec_flops", "fq3_codec_launch_count",
     "fq3_codec_destroy", "fq3_codec_last_error",
 ]
@@ -117,6 +117,8 @@ def load_library() -> C.CDLL:
     lib.fq3_tape_bytes.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     lib.fq3_num_ctas.argtypes = [C.c_void_p]
     lib.fq3_barrier_test.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
+    lib.fq3_engine_set_prefill_weights.argtypes = [C.c_void_p, C.POINTER(Tensor), C.c_int32]
+    lib.fq3_prefill.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.fq3_codec_create.argtypes = [C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_void_p)]
     lib.fq3_codec_destroy.argtypes = [C.c_void_p]
     lib.fq3_codec_destroy.restype = None
@@ -190,6 +192,8 @@ class Engine:
         self.H = talker["hidden_size"]
         self._keep = {}  # tensors borrowed by the engine for the duration of a request
         self.loaded = False
+        self.has_prefill = False
+        self._prefill_keep = None
         self.time_kernels = False   # bench: CUDA-event time of every decode_chunk launch
         self.last_kernel_ms = None
 
@@ -220,6 +224,26 @@ class Engine:
         with torch.cuda.device(self.device):
             _check(self.lib, self.lib.fq3_engine_load_weights(self.h, arr, len(tensors), self._stream()))
         self.loaded = True
+
+    # -- K3 prefill -------------------------------------------------------------------------------------
+    def set_prefill_weights(self, tensors: Dict[str, torch.Tensor]):
+        """Row-major bf16 weights borrowed by the hand-written prefill (kept alive here)."""
+        keep = {k: self._t(v) for k, v in tensors.items()}
+        arr = (Tensor * len(keep))()
+        for i, (k, v) in enumerate(keep.items()):
+            arr[i] = Tensor(k.encode(), v.data_ptr(), v.numel())
+        _check(self.lib, self.lib.fq3_engine_set_prefill_weights(self.h, arr, len(keep)))
+        self._prefill_keep = keep
+        self.has_prefill = True
+
+    def prefill(self, embeds: torch.Tensor, n_left_pad: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
+        """embeds [P,H] -> (logits [V], past_hidden [H]); KV slots [0,P) are written in the engine cache."""
+        x = self._t(embeds.reshape(-1, self.H))
+        logits = torch.empty(self.talker_cfg["vocab_size"], dtype=self.dtype, device=self.device)
+        hidden = torch.empty(self.H, dtype=self.dtype, device=self.device)
+        _check(self.lib, self.lib.fq3_prefill(self.h, x.data_ptr(), x.shape[0], int(n_left_pad), logits.data_ptr(),
+                                              hidden.data_ptr(), self._stream()))
+        return logits, hidden
 
     # -- duck-type path ----------------------------------------------------------------------------------
     def import_kv(self, layer: int, k: torch.Tensor, v: torch.Tensor):

@@ -41,7 +41,17 @@ def begin_fused(engine, talker, tie, tam, tth, tpe, config, predictor_graph, tal
                 min_new_tokens, temperature, top_k, top_p, do_sample, repetition_penalty, uniforms):
     """Prefill + first token + request latch (generate.py:104-140).  Returns the first token id."""
     eos_id = config.codec_eos_token_id
-    out = _prefill(talker, tie, tam, tth, tpe)
+    native = getattr(engine, "has_prefill", False) and getattr(talker_graph, "use_native_prefill", True) \
+        and tie.shape[0] == 1
+    if native:
+        # K3: hand-written prefill writes the KV cache directly (no talker.forward, no prefill_kv copies)
+        pad = int((tam[0] == 0).sum().item()) if tam is not None else 0
+        lg, ph = engine.prefill(tie[0], pad)
+        import types
+        out = types.SimpleNamespace(logits=lg.view(1, 1, -1), past_hidden=ph.view(1, 1, -1), generation_step=0,
+                                    past_key_values=None)
+    else:
+        out = _prefill(talker, tie, tam, tth, tpe)
     sp_t = SamplingParams(do_sample=do_sample, top_k=top_k, temperature=temperature, top_p=top_p,
                           repetition_penalty=repetition_penalty)
     if (do_sample or predictor_graph.do_sample) and uniforms is None:
@@ -49,8 +59,13 @@ def begin_fused(engine, talker, tie, tam, tth, tpe, config, predictor_graph, tal
     u0 = float(uniforms.reshape(-1)[0]) if (do_sample and uniforms is not None) else 0.0
     first = engine.sample_logits(out.logits[:, -1, :], SamplingParams(do_sample, top_k, temperature, top_p, 1.0), u=u0,
                                  suppress_special=True, eos_id=eos_id, suppress_eos=min_new_tokens > 0)
-    prefill_len = talker_graph.prefill_kv(out.past_key_values)
-    talker_graph.set_generation_state(tam, getattr(talker, "rope_deltas", None))
+    if native:
+        prefill_len = int(tie.shape[1])
+        talker_graph.prefill_len = prefill_len
+        talker_graph.set_generation_state(tam, torch.tensor([-pad]) if pad else None)
+    else:
+        prefill_len = talker_graph.prefill_kv(out.past_key_values)
+        talker_graph.set_generation_state(tam, getattr(talker, "rope_deltas", None))
     gen_step = int(out.generation_step) if out.generation_step is not None else 0
     engine.begin_request(first_token=int(first.item()), prefill_len=prefill_len, gen_step=gen_step,
                          past_hidden=out.past_hidden, trailing_text=tth, tts_pad=tpe, max_new_tokens=max_new_tokens,

@@ -28,6 +28,7 @@ class TalkerGraph:
             self.hidden_size = engine.talker_cfg["hidden_size"]
             self.num_layers = engine.talker_cfg["num_hidden_layers"]
         self.captured = False
+        self.use_native_prefill = True   # K3 (bf16 engines); False -> talker.forward + prefill_kv like the reference
         self.prefill_len = 0
         self.n_left_pad = 0
         self.rope_delta = 0

@@ -98,7 +98,8 @@ def engine_tensors(talker, talker_cfg: dict, pred_cfg: dict, dtype, device, rope
     return out
 
 
-def engine_for_talker(talker, dtype=torch.bfloat16, device="cuda", max_seq_len: int = 2048, num_ctas: int = 0):
+def engine_for_talker(talker, dtype=torch.bfloat16, device="cuda", max_seq_len: int = 2048, num_ctas: int = 0,
+                      native_prefill: bool = True):
     """Build and load an fq3 Engine from the upstream talker module (``base_model.model.talker``)."""
     from .engine import Engine
 
@@ -110,5 +111,15 @@ def engine_for_talker(talker, dtype=torch.bfloat16, device="cuda", max_seq_len: 
                  num_code_groups=int(_cfg_get(tcfg_obj, "num_code_groups", 16)),
                  codec_eos_token_id=int(_cfg_get(tcfg_obj, "codec_eos_token_id")),
                  has_mtp_projection=has_mtp_projection(talker.code_predictor), num_ctas=num_ctas)
-    eng.load_weights(engine_tensors(talker, tcfg, pcfg, dtype, eng.device, eng.rope_positions))
+    tensors = engine_tensors(talker, tcfg, pcfg, dtype, eng.device, eng.rope_positions)
+    eng.load_weights(tensors)
+    if dtype == torch.bfloat16 and native_prefill:
+        L, I, H = tcfg["num_hidden_layers"], tcfg["intermediate_size"], tcfg["hidden_size"]
+        eng.set_prefill_weights({
+            "t.qkv": torch.cat((tensors["t.q"], tensors["t.k"], tensors["t.v"]), dim=1).contiguous(),
+            "t.o": tensors["t.o"],
+            "t.gu": torch.stack((tensors["t.gate"], tensors["t.up"]), dim=2).reshape(L, 2 * I, H).contiguous(),
+            "t.down": tensors["t.down"],
+            "t.head": tensors["t.head"],
+        })
     return eng

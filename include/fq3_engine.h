@@ -138,6 +138,16 @@ int fq3_sample_logits(fq3_engine* e, const void* logits_dev, int32_t V, const fq
                       const int64_t* history_dev, int32_t n_hist, int32_t suppress_special, int32_t eos_id,
                       int32_t suppress_eos, int64_t* token_out_dev, void* stream);
 
+/* ---- K3: hand-written prefill (bf16 engines) ------------------------------------------------------------------ */
+/* Borrow row-major weights for the prompt GEMMs (caller keeps them alive): t.qkv [L,(nH+2nKV)*128,H] (q,k,v rows
+ * concatenated), t.o [L,H,nH*128], t.gu [L,2I,H] (gate/up rows interleaved), t.down [L,H,I], t.head [V,H]. */
+int fq3_engine_set_prefill_weights(fq3_engine* e, const fq3_tensor* tensors, int32_t n);
+/* talker.forward prefill (generate.py:107-118) + TalkerGraph.prefill_kv (talker_graph.py:153-170) in one call:
+ * embeds_dev [P,H] -> KV cache slots [0,P), logits_out_dev [V] (codec_head on the last position), hidden_out_dev [H]
+ * (post-norm hidden of the last position = past_hidden).  Positions are slot - n_left_pad (clamped at 0). */
+int fq3_prefill(fq3_engine* e, const void* embeds_dev, int32_t P, int32_t n_left_pad, void* logits_out_dev,
+                void* hidden_out_dev, void* stream);
+
 /* ---- fused path (the persistent on-device loop) ---------------------------------------------------------- */
 /* generate.py:120-147 / streaming.py:76-104: latch per-request state.  past_hidden_dev [H] model dtype;
  * trailing_text_dev [trailing_len,H], tts_pad_dev [H] model dtype (borrowed until the request ends);
