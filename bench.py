@@ -34,6 +34,7 @@ for p in (ROOT, os.path.join(ROOT, "faster-qwen3-tts_b200"), os.path.join(ROOT, 
     if p not in sys.path:
         sys.path.insert(0, p)
 
+os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the single JSON line (NCCL is only used for the timing barrier)
 import torch  # noqa: E402
 
 FRAME_S = 0.08  # 1920 samples @ 24 kHz (ggml_backend.py:22)

@@ -25,6 +25,9 @@
 
 #include "../../include/fq3_engine.h"
 #include "fq3_gemm.cuh"
+#include "fq3_gemm_tc.cuh"
+
+extern int g_fq3_gemm_backend;  // 0 = tcgen05/TMA kernel when the shape allows, 1 = force the mma.sync kernel
 
 namespace {
 
@@ -269,9 +272,14 @@ static int launch_conv(fq3_codec* c, const Layer& L, const __nv_bfloat16* X, con
   a.X = X; a.W = L.W; a.bias = L.bias; a.R = R; a.Yraw = Yraw; a.Yact = Yact; a.ea = L.ea; a.ib = L.ib;
   a.T = T; a.Cin = L.Cin; a.N = L.N; a.taps = L.taps; a.dil = L.dil; a.bias_mod = L.bias_mod; a.act_mod = L.act_mod;
   a.mode = 0;
+  c->launches++;
+  if (g_fq3_gemm_backend == 0) {
+    const int r = fq3tc::launch_tc(a, stream);
+    if (r == 0) return 0;
+    if (r < 0) return cfail(FQ3_ERR_CUDA, "tcgen05 conv launch failed: ", cudaGetErrorString(cudaGetLastError()));
+  }
   dim3 grid((T + BM - 1) / BM, (L.N + BN - 1) / BN);
   conv_gemm_kernel<<<grid, CTHREADS, CONV_SMEM, stream>>>(a);
-  c->launches++;
   CCK(cudaGetLastError());
   return 0;
 }

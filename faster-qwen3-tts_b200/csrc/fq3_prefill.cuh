@@ -9,6 +9,7 @@
 // residual.  GEMMs are the shared implicit-GEMM tensor-core kernel (fq3_gemm.cuh, taps = 1).
 #pragma once
 #include "fq3_gemm.cuh"
+#include "fq3_gemm_tc.cuh"
 
 namespace pf {
 
@@ -165,9 +166,14 @@ static int pf_gemm(fq3_engine* e, const __nv_bfloat16* X, const __nv_bfloat16* W
   memset(&a, 0, sizeof(a));
   a.X = X; a.W = W; a.R = R; a.Yraw = Y; a.T = T; a.Cin = K; a.N = N; a.taps = 1; a.dil = 1;
   a.bias_mod = 1; a.act_mod = 1; a.mode = mode;
+  e->launches++;
+  if (g_fq3_gemm_backend == 0) {
+    const int r = fq3tc::launch_tc(a, stream);
+    if (r == 0) return 0;
+    if (r < 0) return fail(FQ3_ERR_CUDA, "tcgen05 GEMM launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+  }
   dim3 grid((T + fq3gemm::BM - 1) / fq3gemm::BM, (N + fq3gemm::BN - 1) / fq3gemm::BN);
   fq3gemm::conv_gemm_kernel<<<grid, fq3gemm::CTHREADS, fq3gemm::CONV_SMEM, stream>>>(a);
-  e->launches++;
   CK(cudaGetLastError());
   return 0;
 }

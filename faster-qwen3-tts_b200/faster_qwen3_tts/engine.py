@@ -61,7 +61,7 @@ EXPORTS = [
     "fq3_engine_create", "fq3_engine_load_weights", "fq3_engine_destroy", "fq3_import_kv",
     "fq3_set_generation_state", "fq3_talker_step", "fq3_predictor_run", "fq3_sample_logits", "fq3_begin_request",
     "fq3_decode_chunk", "fq3_get_past_hidden", "fq3_debug_enable", "fq3_debug_read", "fq3_tape_bytes",
-    "fq3_num_ctas", "fq3_launch_count", "fq3_last_error", "fq3_version", "fq3_barrier_test", "fq3_engine_set_prefill_weights", "fq3_prefill",
+    "fq3_num_ctas", "fq3_launch_count", "fq3_last_error", "fq3_version", "fq3_barrier_test", "fq3_engine_set_prefill_weights", "fq3_prefill", "fq3_set_gemm_backend",
     "fq3_codec_create", "fq3_codec_load_weights", "fq3_codec_decode", "fq3_codec_flops", "fq3_codec_launch_count",
     "fq3_codec_destroy", "fq3_codec_last_error",
 ]
@@ -117,6 +117,7 @@ def load_library() -> C.CDLL:
     lib.fq3_tape_bytes.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     lib.fq3_num_ctas.argtypes = [C.c_void_p]
     lib.fq3_barrier_test.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
+    lib.fq3_set_gemm_backend.argtypes = [C.c_int32]
     lib.fq3_engine_set_prefill_weights.argtypes = [C.c_void_p, C.POINTER(Tensor), C.c_int32]
     lib.fq3_prefill.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.fq3_codec_create.argtypes = [C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_void_p)]
@@ -131,6 +132,11 @@ def load_library() -> C.CDLL:
     lib.fq3_codec_last_error.restype = C.c_char_p
     _lib = lib
     return lib
+
+
+def set_gemm_backend(name: str):
+    """'tcgen05' (default) or 'mma' for the dense layers of K3 (prefill) and K4 (codec)."""
+    load_library().fq3_set_gemm_backend(0 if name == "tcgen05" else 1)
 
 
 class EngineError(RuntimeError):

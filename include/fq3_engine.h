@@ -187,6 +187,10 @@ int64_t fq3_codec_launch_count(fq3_codec* c);
 void fq3_codec_destroy(fq3_codec* c);
 const char* fq3_codec_last_error(void);
 
+/* dense-layer kernel selection for K3/K4: 0 = tcgen05 + TMA implicit GEMM when the shape allows (default),
+ * 1 = always the mma.sync kernel (A/B reference). */
+int fq3_set_gemm_backend(int32_t backend);
+
 const char* fq3_last_error(void);
 const char* fq3_version(void);
 
