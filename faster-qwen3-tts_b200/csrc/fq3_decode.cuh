@@ -236,6 +236,23 @@ __device__ __forceinline__ void grid_sync(Ctx& c) {
   csync();
 }
 
+// split form: everything issued between grid_arrive() and grid_wait() overlaps the barrier latency -- used for loads
+// that do not depend on other CTAs' results of the current phase (cached K/V rows, norm weights)
+__device__ __forceinline__ void grid_arrive(Ctx& c) {
+  csync();
+  if (c.tid == 0) {
+    c.bar_target += (unsigned)c.P.ncta;
+    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(c.P.bar), "r"(1u) : "memory");
+  }
+}
+__device__ __forceinline__ void grid_wait(Ctx& c) {
+  if (c.tid == 0) {
+    while (ld_acquire_u32(c.P.bar) < c.bar_target) {
+    }
+  }
+  csync();
+}
+
 // experimental variants measured by tools/microbench.py (MODE_BARRIER_TEST)
 __device__ __forceinline__ void grid_sync_v1(Ctx& c) {  // release-reduction + acquire-poll, no separate fences
   csync();
@@ -1073,8 +1090,33 @@ __device__ __forceinline__ float xs_get(Ctx& c, int idx) {
 // ------------------------------------------------------------------------------------------------------------
 // NT == 2 is the predictor prefill (slot0 == 0: no cached keys at all); NT == 1 the single-token passes.
 // Register budget is 168/thread (9 warps per SM), so K rows and V rows are fetched in two round trips.
+template <bool BF>
+struct SmallKV {  // cached K/V rows of this warp's kv group, fetched in the shadow of the QKV barrier
+  using Raw = typename std::conditional<BF, uint2, float4>::type;
+  Raw k[16], v[16];
+};
+template <bool BF>
+__device__ __forceinline__ void small_kv_preload(Ctx& c, const StackDev& S, int layer, int slot0, SmallKV<BF>& pre) {
+  using Raw = typename SmallKV<BF>::Raw;
+  const size_t esz = BF ? 2 : 4;
+  const int g = c.warp < S.nKV ? c.warp : 0;
+  const uint8_t* kb = reinterpret_cast<const uint8_t*>(S.kc) + ((size_t)(layer * S.nKV + g) * S.S * 128) * esz;
+  const uint8_t* vb = reinterpret_cast<const uint8_t*>(S.vc) + ((size_t)(layer * S.nKV + g) * S.S * 128) * esz;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    if (j < slot0) {
+      pre.k[j] = __ldcg(reinterpret_cast<const Raw*>(kb + (size_t)j * 128 * esz) + c.lane);
+      pre.v[j] = __ldcg(reinterpret_cast<const Raw*>(vb + (size_t)j * 128 * esz) + c.lane);
+    } else {
+      if constexpr (BF) { pre.k[j] = make_uint2(0, 0); pre.v[j] = make_uint2(0, 0); }
+      else { pre.k[j] = make_float4(0, 0, 0, 0); pre.v[j] = make_float4(0, 0, 0, 0); }
+    }
+  }
+}
+
 template <bool BF, int NT>
-__device__ void attention_small_all(Ctx& c, const StackDev& S, int layer, int slot0_, int rpos0) {
+__device__ void attention_small_all(Ctx& c, const StackDev& S, int layer, int slot0_, int rpos0,
+                                    const SmallKV<BF>* pre = nullptr) {
   const KParams& P = c.P;
   constexpr int NOLD = NT == 2 ? 1 : 16;  // cached keys that can exist
   constexpr int MAXK = NT == 2 ? 2 : 17;
@@ -1098,7 +1140,8 @@ __device__ void attention_small_all(Ctx& c, const StackDev& S, int layer, int sl
     Raw kraw[NOLD];
 #pragma unroll
     for (int j = 0; j < NOLD; ++j) {
-      if (j < slot0) kraw[j] = __ldcg(reinterpret_cast<const Raw*>(kb + (size_t)j * 128 * esz) + c.lane);
+      if (pre && NT == 1 && g == c.warp) kraw[j] = pre->k[j];
+      else if (j < slot0) kraw[j] = __ldcg(reinterpret_cast<const Raw*>(kb + (size_t)j * 128 * esz) + c.lane);
       else zero_raw(kraw[j]);
     }
     float4 qn4, kn4, cs4[NT], sn4[NT], kr4[NT], vr4[NT], qr4[2][NT];
@@ -1198,7 +1241,8 @@ __device__ void attention_small_all(Ctx& c, const StackDev& S, int layer, int sl
     Raw vraw[NOLD];
 #pragma unroll
     for (int j = 0; j < NOLD; ++j) {
-      if (j < slot0) vraw[j] = __ldcg(reinterpret_cast<const Raw*>(vb + (size_t)j * 128 * esz) + c.lane);
+      if (pre && NT == 1 && g == c.warp) vraw[j] = pre->v[j];
+      else if (j < slot0) vraw[j] = __ldcg(reinterpret_cast<const Raw*>(vb + (size_t)j * 128 * esz) + c.lane);
       else zero_raw(vraw[j]);
     }
     // softmax with the keys distributed over lanes: every lane knows all scores (max is redundant and cheap), but
@@ -1260,10 +1304,21 @@ __device__ void attention_small_all(Ctx& c, const StackDev& S, int layer, int sl
 }
 
 // RMSNorm of a vector (global fp32 or shared fp32) into the staging vector at element offset `off`
+constexpr int NORM_E = HMAX / NCT;
+// norm weights of one vector into registers (issued in the shadow of a barrier: they are touched once per pass and
+// usually miss to HBM, while the activations they scale arrive from L2)
+template <bool BF>
+__device__ __forceinline__ void norm_wload(Ctx& c, const void* w, size_t woff, int H, float* wv) {
+#pragma unroll
+  for (int i = 0; i < NORM_E; ++i) {
+    const int k = c.tid + i * NCT;
+    wv[i] = k < H ? ldw<BF>(w, woff + k) : 0.f;
+  }
+}
 template <bool BF>
 __device__ __forceinline__ void norm_stage(Ctx& c, const float* src, bool src_smem, const void* w, size_t woff, int H,
-                                           float eps, int off) {
-  constexpr int MAXE = HMAX / NCT;
+                                           float eps, int off, const float* wpre = nullptr) {
+  constexpr int MAXE = NORM_E;
   float v[MAXE], wv[MAXE];
 #pragma unroll
   for (int i = 0; i < MAXE; ++i) {
@@ -1272,7 +1327,7 @@ __device__ __forceinline__ void norm_stage(Ctx& c, const float* src, bool src_sm
     wv[i] = 0.f;
     if (k < H) {
       v[i] = src_smem ? src[k] : __ldcg(src + k);
-      wv[i] = ldw<BF>(w, woff + k);
+      wv[i] = wpre ? wpre[i] : ldw<BF>(w, woff + k);
     }
   }
   float ss = 0.f;
@@ -1301,28 +1356,34 @@ __device__ void run_layers(Ctx& c, const StackDev& S, int nt, int slot0, int rpo
   int pi = 0;
   dbg = dbg && (P.dbg_on & 1);
   auto nopre = [](int, int) { return 0.f; };
+  float wnext[NORM_E];  // norm weights of the NEXT norm, fetched while the preceding barrier is in flight
   for (int l = 0; l < S.L; ++l) {
     probe(c, pi);  // 0: layer start
     // ---- P1: input norm + QKV rows
     for (int t = 0; t < nt; ++t) {
-      if (l == 0 && x0_local) norm_stage<BF>(c, c.s.xin[t], true, S.ln_in, (size_t)l * S.H, S.H, S.eps, t * S.H);
-      else norm_stage<BF>(c, P.X + (size_t)t * P.ldX, false, S.ln_in, (size_t)l * S.H, S.H, S.eps, t * S.H);
+      const float* wp = l > 0 ? wnext : nullptr;
+      if (l == 0 && x0_local) norm_stage<BF>(c, c.s.xin[t], true, S.ln_in, (size_t)l * S.H, S.H, S.eps, t * S.H, wp);
+      else norm_stage<BF>(c, P.X + (size_t)t * P.ldX, false, S.ln_in, (size_t)l * S.H, S.H, S.eps, t * S.H, wp);
     }
     probe(c, pi);  // 1: after input norm
     gemv_any<BF, false>(c, S.seg_base + 4 * l + 0, nt, S.H, nopre,
                         [&](int row, int t, float v, float, float) { P.QKV[(size_t)t * P.ldQKV + row] = rnd<BF>(v); });
     probe(c, pi);  // 2: after QKV gemv
-    grid_sync(c);
+    const bool small_attn = !is_talker && S.S <= 32 && S.rep <= 2 && ((nt == 1 && slot0 <= 16) || (nt == 2 && slot0 == 0));
+    const bool kv_pre = small_attn && nt == 1 && S.nKV <= NCW;
+    SmallKV<BF> skv;
+    grid_arrive(c);
+    if (kv_pre) small_kv_preload<BF>(c, S, l, slot0, skv);  // cached keys/values do not depend on this layer's QKV
+    grid_wait(c);
     probe(c, pi);  // 3: after B1
     if (dbg && cta0) {
       float* d = P.dbg + (size_t)l * P.dbg_stride_layer;
       for (int t = 0; t < nt; ++t)
         for (int k = c.tid; k < S.qd + 2 * S.kd; k += NCT) d[(size_t)t * (S.qd + 2 * S.kd) + k] = __ldcg(P.QKV + (size_t)t * P.ldQKV + k);
     }
-    const bool small_attn = !is_talker && S.S <= 32 && S.rep <= 2 && ((nt == 1 && slot0 <= 16) || (nt == 2 && slot0 == 0));
     if (small_attn) {
       // ---- P2+P3 fused: redundant small attention straight into the staging vector (no exchange, no barrier)
-      if (nt == 1) attention_small_all<BF, 1>(c, S, l, slot0, rpos0);
+      if (nt == 1) attention_small_all<BF, 1>(c, S, l, slot0, rpos0, kv_pre ? &skv : nullptr);
       else attention_small_all<BF, 2>(c, S, l, slot0, rpos0);
       probe(c, pi);  // 4
       probe(c, pi);  // 5
@@ -1369,11 +1430,14 @@ __device__ void run_layers(Ctx& c, const StackDev& S, int nt, int slot0, int rpo
           [&](int row, int t, float v, float, float res) { P.X1[(size_t)t * P.ldX + row] = rnd<BF>(res + rnd<BF>(v)); });
     }
     probe(c, pi);  // 6: after O gemv
-    grid_sync(c);
+    float wpost[NORM_E];
+    grid_arrive(c);
+    norm_wload<BF>(c, S.ln_post, (size_t)l * S.H, S.H, wpost);
+    grid_wait(c);
     probe(c, pi);  // 7: after B3
     // ---- P4: post-attention norm + gate/up rows + SiLU*up
     for (int t = 0; t < nt; ++t)
-      norm_stage<BF>(c, P.X1 + (size_t)t * P.ldX, false, S.ln_post, (size_t)l * S.H, S.H, S.eps, t * S.H);
+      norm_stage<BF>(c, P.X1 + (size_t)t * P.ldX, false, S.ln_post, (size_t)l * S.H, S.H, S.eps, t * S.H, wpost);
     if (dbg && cta0) {
       float* d = P.dbg + (size_t)l * P.dbg_stride_layer + (size_t)2 * (S.qd + 2 * S.kd) + 2 * S.qd;
       for (int t = 0; t < nt; ++t)
@@ -1399,7 +1463,10 @@ __device__ void run_layers(Ctx& c, const StackDev& S, int nt, int slot0, int rpo
         c, S.seg_base + 4 * l + 3, nt, S.I, [&](int row, int t) { return __ldcg(P.X1 + (size_t)t * P.ldX + row); },
         [&](int row, int t, float v, float, float res) { P.X[(size_t)t * P.ldX + row] = rnd<BF>(res + rnd<BF>(v)); });
     probe(c, pi);  // 10: after DN gemv
-    grid_sync(c);
+    grid_arrive(c);
+    if (l + 1 < S.L) norm_wload<BF>(c, S.ln_in, (size_t)(l + 1) * S.H, S.H, wnext);
+    else norm_wload<BF>(c, S.ln_f, 0, S.H, wnext);
+    grid_wait(c);
     probe(c, pi);  // 11: after B5
     if (dbg && cta0) {
       float* d = P.dbg + (size_t)l * P.dbg_stride_layer + (size_t)2 * (S.qd + 2 * S.kd) + 2 * S.qd + 2 * S.H + 2 * S.I;
@@ -1408,7 +1475,7 @@ __device__ void run_layers(Ctx& c, const StackDev& S, int nt, int slot0, int rpo
     }
   }
   // final norm of the last token -> staging vector [0..H)
-  norm_stage<BF>(c, P.X + (size_t)(nt - 1) * P.ldX, false, S.ln_f, 0, S.H, S.eps, 0);
+  norm_stage<BF>(c, P.X + (size_t)(nt - 1) * P.ldX, false, S.ln_f, 0, S.H, S.eps, 0, wnext);
 }
 
 // head GEMV (rows of a [V,H] matrix) on the staging vector -> LOGITS, then grid barrier
