@@ -56,7 +56,7 @@ def parse():
     ap.add_argument("--no-codec", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--num-ctas", type=int, default=0)
-    ap.add_argument("--cpu-frames", type=int, default=8)
+    ap.add_argument("--cpu-frames", type=int, default=64)
     return ap.parse_args()
 
 
@@ -107,7 +107,9 @@ def cpu_oracle_run(args, frames: int):
     fp32 on this host, measured 479 s for the same sample -- dynamic KV, all host threads).
     Returns (rtf, seconds, threads, description)."""
     from oracle import qwen3_tts_oracle as O
-    nthreads = os.cpu_count() or 1
+    # torch-eager GEMV chains stop scaling (and collapse under OpenMP oversubscription: 479 s for this sample with 128
+    # threads on the GPU box vs 3 s with 8 threads) -- use at most 16 threads and report the number used
+    nthreads = min(os.cpu_count() or 1, 16)
     torch.set_num_threads(nthreads)
     cfg = O.cfg_1p7b() if args.size == "1.7B" else O.cfg_0p6b()
     # cheap deterministic weights (values do not matter for timing; shapes/dtype do)
@@ -328,11 +330,20 @@ def run_b200(args):
     b_alg = t_bytes + kv_bytes + pred_layers + pred_heads + mtp
     b_stream = t_bytes + kv_bytes + p_bytes
     k_ms = statistics.mean(chunk_ms) if chunk_ms else None
+    traffic = None
+    try:  # DRAM bytes of one launch from the committed ncu capture of this kernel (profiles/)
+        for line in open(os.path.join(ROOT, "profiles", "r1b_decode_kernel_ncu.csv")):
+            f = line.strip().split(",")
+            if len(f) == 4 and f[0] == "0" and f[1] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                traffic = (traffic or 0.0) + float(f[3]) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[f[2]]
+    except Exception:
+        traffic = None
     roof = None
     if k_ms:
         ach = b_alg * args.chunk / (k_ms / 1000) / 1e9
         roof = {"bound": "hbm", "kernel": "fq3_decode_kernel<bf16> (one launch = one 8-frame chunk)",
-                "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
+                "traffic_source": "ncu --set full capture of one 8-frame launch, profiles/r1b_decode_kernel_ncu.csv",
                 "peak_source": peak_kind, "alg_bytes_per_frame": b_alg, "launch_ms": k_ms,
                 "streamed_bytes_per_frame": b_stream, "streamed_frac": b_stream * args.chunk / (k_ms / 1000) / 1e9 / peak,
                 "ms_per_frame": k_ms / args.chunk}

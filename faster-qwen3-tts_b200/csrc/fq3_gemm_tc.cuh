@@ -21,14 +21,15 @@ namespace fq3tc {
 constexpr int TBM = 128, TBN = 96, TTHREADS = 192;
 constexpr int TMEM_COLS = 128;
 
-template <int BK>
+// DEEP = 1: grids that do not fill the machine (<= one CTA per SM) get a deep ring (latency-bound main loop);
+// DEEP = 0: large grids get small rings so 2-4 CTAs co-reside per SM and overlap each other's prologue / epilogue.
+template <int BK, int DEEP>
 struct Cfg {
   static constexpr int A_BYTES = TBM * BK * 2;
   static constexpr int B_BYTES = TBN * BK * 2;
   static constexpr int STAGE = A_BYTES + B_BYTES;
-  static constexpr int STAGES = BK == 64 ? 3 : 4;   // small rings: 2 (BK=64) / 3-4 (BK=32) CTAs co-reside per SM so
-                                                    // one CTA's prologue / epilogue overlaps another's main loop
-  static constexpr int SMEM = STAGES * STAGE + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int STAGES = DEEP ? (BK == 64 ? 7 : 12) : (BK == 64 ? 3 : 4);
+  static constexpr int SMEM = STAGES * STAGE + 1024 /*align slack*/ + 256 /*barriers*/ + 3 * TBN * 4 /*epilogue params*/;
   static constexpr uint32_t SBO = (8 * BK * 2) >> 4;          // 8-row group stride, 16-byte units
   static constexpr uint64_t LAYOUT = BK == 64 ? 2ull : 4ull;  // SWIZZLE_128B : SWIZZLE_64B
 };
@@ -85,17 +86,18 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
       : "r"(taddr));
 }
 
-template <int BK>
-static __global__ void __launch_bounds__(TTHREADS, 2)
+template <int BK, int DEEP>
+static __global__ void __launch_bounds__(TTHREADS, DEEP ? 1 : 2)
     conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
                         const __grid_constant__ fq3gemm::ConvArgs a) {
-  using C = Cfg<BK>;
+  using C = Cfg<BK, DEEP>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* full = reinterpret_cast<uint64_t*>(tiles + C::STAGES * C::STAGE);
   uint64_t* empty = full + C::STAGES;
   uint64_t* accum = empty + C::STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum + 1);
+  float* ep = reinterpret_cast<float*>(tiles + C::STAGES * C::STAGE + 256);  // [3][TBN]: bias, exp(alpha), 1/(exp(beta)+eps)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * TBM, n0 = blockIdx.y * TBN;
   const int kc = a.Cin / BK, nks = a.taps * kc;
@@ -150,6 +152,16 @@ static __global__ void __launch_bounds__(TTHREADS, 2)
     }
   } else {
     // ===================== epilogue (warps 2..5) =====================
+    // per-column parameters of this tile go to shared memory while the main loop runs (no modulo / dependent global
+    // loads on the critical path after the accumulator is ready)
+    for (int i = threadIdx.x - 64; i < TBN; i += 128) {
+      const int n = n0 + i;
+      const bool ok = n < a.N && a.mode == 0;
+      ep[i] = (ok && a.bias) ? a.bias[n % a.bias_mod] : 0.f;
+      ep[TBN + i] = (ok && a.Yact) ? a.ea[n % a.act_mod] : 0.f;
+      ep[2 * TBN + i] = (ok && a.Yact) ? a.ib[n % a.act_mod] : 0.f;
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
     mb_wait(accum, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
@@ -187,10 +199,8 @@ static __global__ void __launch_bounds__(TTHREADS, 2)
             float v[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[j][h * 8 + i]);
-            if (a.bias) {
 #pragma unroll
-              for (int i = 0; i < 8; ++i) v[i] += a.bias[(n + i) % a.bias_mod];
-            }
+            for (int i = 0; i < 8; ++i) v[i] += ep[j * 32 + h * 8 + i];
             if (a.R) {
               const uint4 rr = *reinterpret_cast<const uint4*>(a.R + off + j * 32 + h * 8);
               const __nv_bfloat16* rb = reinterpret_cast<const __nv_bfloat16*>(&rr);
@@ -206,9 +216,9 @@ static __global__ void __launch_bounds__(TTHREADS, 2)
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
                 const float x = __bfloat162float(raw[i]);
-                const int c = (n + i) % a.act_mod;
-                const float sn = __sinf(x * a.ea[c]);
-                act[i] = __float2bfloat16_rn(x + a.ib[c] * sn * sn);
+                const int cidx = j * 32 + h * 8 + i;
+                const float sn = __sinf(x * ep[TBN + cidx]);
+                act[i] = __float2bfloat16_rn(x + ep[2 * TBN + cidx] * sn * sn);
               }
               *reinterpret_cast<uint4*>(a.Yact + off + j * 32 + h * 8) = *reinterpret_cast<const uint4*>(act);
             }
@@ -255,9 +265,15 @@ static bool make_map(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t 
 // returns 0 on success, 1 if this shape must use the mma.sync fallback, <0 on CUDA error
 static int launch_tc(const fq3gemm::ConvArgs& a, cudaStream_t stream) {
   static bool attr_done = false;
+  static int num_sms = 148;
   if (!attr_done) {
-    if (cudaFuncSetAttribute(conv_gemm_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<64>::SMEM) != cudaSuccess) return -1;
-    if (cudaFuncSetAttribute(conv_gemm_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<32>::SMEM) != cudaSuccess) return -1;
+    if (cudaFuncSetAttribute(conv_gemm_tc_kernel<64, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<64, 0>::SMEM) != cudaSuccess) return -1;
+    if (cudaFuncSetAttribute(conv_gemm_tc_kernel<32, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<32, 0>::SMEM) != cudaSuccess) return -1;
+    if (cudaFuncSetAttribute(conv_gemm_tc_kernel<64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<64, 1>::SMEM) != cudaSuccess) return -1;
+    if (cudaFuncSetAttribute(conv_gemm_tc_kernel<32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<32, 1>::SMEM) != cudaSuccess) return -1;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
     attr_done = true;
   }
   const int BK = (a.Cin % 64 == 0) ? 64 : ((a.Cin % 32 == 0) ? 32 : 0);
@@ -268,8 +284,14 @@ static int launch_tc(const fq3gemm::ConvArgs& a, cudaStream_t stream) {
   if (!make_map(&tmX, a.X, (uint64_t)a.T, (uint64_t)a.Cin, TBM, BK)) return 1;
   if (!make_map(&tmW, a.W, (uint64_t)a.N, (uint64_t)a.taps * a.Cin, TBN, BK)) return 1;
   dim3 grid((a.T + TBM - 1) / TBM, (a.N + TBN - 1) / TBN);
-  if (BK == 64) conv_gemm_tc_kernel<64><<<grid, TTHREADS, Cfg<64>::SMEM, stream>>>(tmX, tmW, a);
-  else conv_gemm_tc_kernel<32><<<grid, TTHREADS, Cfg<32>::SMEM, stream>>>(tmX, tmW, a);
+  const bool deep = (long long)grid.x * grid.y <= (long long)num_sms * 3 / 2;
+  if (BK == 64) {
+    if (deep) conv_gemm_tc_kernel<64, 1><<<grid, TTHREADS, Cfg<64, 1>::SMEM, stream>>>(tmX, tmW, a);
+    else conv_gemm_tc_kernel<64, 0><<<grid, TTHREADS, Cfg<64, 0>::SMEM, stream>>>(tmX, tmW, a);
+  } else {
+    if (deep) conv_gemm_tc_kernel<32, 1><<<grid, TTHREADS, Cfg<32, 1>::SMEM, stream>>>(tmX, tmW, a);
+    else conv_gemm_tc_kernel<32, 0><<<grid, TTHREADS, Cfg<32, 0>::SMEM, stream>>>(tmX, tmW, a);
+  }
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
