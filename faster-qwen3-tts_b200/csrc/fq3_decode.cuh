@@ -348,46 +348,6 @@ __device__ __forceinline__ void probe(Ctx& c, int& idx) {
   idx++;
 }
 
-// RMSNorm (transformers Qwen3 RMSNorm: fp32 variance, x*rsqrt(var+eps) -> dtype, weight * that) of a global fp32
-// vector into shared memory.  Every CTA computes it redundantly.
-template <bool BF>
-__device__ __forceinline__ void norm_any(Ctx& c, const float* src, bool src_smem, const void* w, size_t woff, int H,
-                                         float eps, float* dst) {
-  constexpr int MAXE = HMAX / NCT;
-  float v[MAXE], wv[MAXE];
-#pragma unroll
-  for (int i = 0; i < MAXE; ++i) {
-    const int k = c.tid + i * NCT;
-    v[i] = 0.f;
-    wv[i] = 0.f;
-    if (k < H) {
-      v[i] = src_smem ? src[k] : __ldcg(src + k);
-      wv[i] = ldw<BF>(w, woff + k);  // issued together with the activation loads: one memory round trip
-    }
-  }
-  float ss = 0.f;
-#pragma unroll
-  for (int i = 0; i < MAXE; ++i) ss += v[i] * v[i];
-  ss = block_sum(c, ss);
-  const float r = 1.0f / sqrtf(ss / (float)H + eps);
-#pragma unroll
-  for (int i = 0; i < MAXE; ++i) {
-    const int k = c.tid + i * NCT;
-    if (k < H) dst[k] = rnd<BF>(wv[i] * rnd<BF>(v[i] * r));
-  }
-  csync();
-}
-template <bool BF>
-__device__ __forceinline__ void norm_to_smem(Ctx& c, const float* src, const void* w, size_t woff, int H, float eps,
-                                             float* dst) {
-  norm_any<BF>(c, src, false, w, woff, H, eps, dst);
-}
-template <bool BF>
-__device__ __forceinline__ void norm_smem_to_smem(Ctx& c, const float* src, const void* w, size_t woff, int H,
-                                                  float eps, float* dst) {
-  norm_any<BF>(c, src, true, w, woff, H, eps, dst);
-}
-
 // ------------------------------------------------------------------------------------------------------------
 // GEMV over one segment: rows of this CTA, streamed from the ring.  x: shared memory, NT vectors of stride xstride.
 // Epilogue epi(row0, v0[NT], v1[NT]) is called by lane 0 for each row pair (rows row0, row0+1).

@@ -130,6 +130,10 @@ class FasterQwen3TTS:
         from . import synthetic
         from .codec import build_codec
         cfg = synthetic.make_config(size)
+        if codec_config is None and size == "tiny":
+            from .codec import Code2WavConfig
+            codec_config = Code2WavConfig(codebook_size=256, hidden_size=256, num_hidden_layers=2, num_attention_heads=4,
+                                          intermediate_size=512, decoder_dim=512)
         st = build_codec(codec_config, seed=seed + 1, dtype=dtype, device=device) if with_codec else None
         base = synthetic.build_base_model(cfg, None, seed=seed, dtype=dtype, device=device, speech_tokenizer=st)
         base.syn_cfg = cfg
@@ -176,7 +180,7 @@ class FasterQwen3TTS:
         tie = torch.randn(1, P, H, generator=g).to(self.dtype)
         tth = torch.randn(1, max(Tt, 1), H, generator=g).to(self.dtype)[:, :Tt]
         tpe = torch.randn(1, 1, H, generator=g).to(self.dtype)
-        ref_codes = torch.randint(0, 2048, (ref_frames, 16), generator=g) if icl else None
+        ref_codes = torch.randint(0, cfg.code_predictor_config.vocab_size, (ref_frames, 16), generator=g) if icl else None
         return (tie.to(dev), torch.ones(1, P, dtype=torch.long, device=dev), tth.to(dev), tpe.to(dev),
                 None if ref_codes is None else ref_codes.to(dev))
 

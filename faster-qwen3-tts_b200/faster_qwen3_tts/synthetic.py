@@ -28,12 +28,15 @@ GEOMETRIES = {
     # name: (talker H, I, L), (predictor H, I, L), has_mtp   -- SURVEY.md App. A
     "1.7B": ((2048, 6144, 28), (1024, 3072, 5), True),
     "0.6B": ((1024, 3072, 28), (1024, 3072, 5), False),
+    "tiny": ((512, 768, 3), (256, 512, 2), True),   # test geometry (4/2 heads, small vocabularies)
 }
 
 
 def make_config(size: str = "1.7B", *, talker_vocab: int = 3072, pred_vocab: int = 2048, eos: int = 2150,
                 heads=(16, 8)) -> types.SimpleNamespace:
     (th, ti, tl), (ph, pi, pl), mtp = GEOMETRIES[size]
+    if size == "tiny":
+        talker_vocab, pred_vocab, eos, heads = 1280, 256, 300, (4, 2)
 
     def stack(h, i, l, v):
         return types.SimpleNamespace(hidden_size=h, intermediate_size=i, num_hidden_layers=l,

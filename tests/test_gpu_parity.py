@@ -303,3 +303,28 @@ def test_native_prefill_vs_oracle_bf16(tiny16):
     p.pg.do_sample = True
     print("native vs module prefill rows equal:", int((a == b).all(dim=1).sum()), "of", a.shape[0])
     assert a.shape == b.shape
+
+
+def test_public_api_end_to_end_tiny():
+    """FasterQwen3TTS public surface on a tiny synthetic model: streaming == non-streaming length bookkeeping, PCM
+    chunk sizes follow the reference's window policy (every chunk is frames*1920 samples), x-vector and ICL modes."""
+    from faster_qwen3_tts import FasterQwen3TTS
+    m = FasterQwen3TTS.from_synthetic("tiny", dtype=torch.bfloat16, max_seq_len=512, seed=3)
+    assert m.sample_rate == 24000
+    for xvec in (True, False):
+        torch.manual_seed(0)
+        chunks = list(m.generate_voice_clone_streaming("hello there general kenobi", "English", ref_audio="ref.wav",
+                                                       ref_text="ref", max_new_tokens=40, min_new_tokens=40, chunk_size=8,
+                                                       xvec_only=xvec))
+        assert len(chunks) == 5
+        for pcm, sr, t in chunks:
+            assert sr == 24000 and pcm.dtype == np.float32 and pcm.shape[0] == t["chunk_steps"] * 1920
+            assert np.isfinite(pcm).all() and np.abs(pcm).max() <= 1.0
+        torch.manual_seed(0)
+        audio, sr = m.generate_voice_clone("hello there general kenobi", "English", ref_audio="ref.wav", ref_text="ref",
+                                           max_new_tokens=40, min_new_tokens=40, xvec_only=xvec)
+        assert sr == 24000 and audio[0].shape[0] == 40 * 1920
+    a, sr = m.generate_custom_voice("good morning", "aiden", "English", max_new_tokens=9, min_new_tokens=9)
+    assert a[0].shape[0] == 9 * 1920
+    with pytest.raises(ValueError, match="ref_audio is required"):
+        m.generate_voice_clone("x", "English")
