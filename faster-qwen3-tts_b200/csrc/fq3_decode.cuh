@@ -82,6 +82,7 @@ struct KParams {
   const void* t_embed;
   const void* p_embeds;
   const void* mtp_b;
+  const void* mtp_tab;   // [ncb][Vp][Hp] = mtp(embeds[i][code]) precomputed at load time (nullptr: project on the fly)
   int has_mtp, ncb, eos;
   int* state;          // [0] token [1] step [2] gen_step [3] finished [4] emitted(last launch)
   float* past_hidden;  // [Ht] fp32 holding dtype-rounded values
@@ -102,6 +103,10 @@ struct KParams {
   int dbg_on;
   long long dbg_stride_layer;  // floats per layer record
   int pred_pin_layers;         // predictor layers whose weights are streamed with L2 evict_last
+  int attn_split;              // talker attention: CTAs per q-head (keys split across them, K/V slices TMA-staged); 0 = off
+  int attn_split_min;          // ... used only when at least this many keys are cached (below, one CTA per q-head is faster)
+  float* PART;                 // [nH][attn_split][PART_STRIDE] partial attention results (acc[128], max, sum)
+  unsigned* attn_cnt;          // [nH] arrival counters of the splits (cleared with the barrier words every launch)
   int mma_tape;                // 1: bf16 tensor-core fragment layout, 0: fp32 row-chunk layout
 };
 
@@ -201,9 +206,14 @@ struct __align__(128) Smem {
   volatile int prod_issued; // tiles issued by the producer
 };
 
+// All dynamic shared memory of the kernel is one Smem; going through this accessor (instead of a reference carried
+// in Ctx) lets the compiler prove the address space everywhere: STS/LDS with 32-bit addresses, not generic ST/LD.
+extern __shared__ __align__(128) uint8_t fq3_smem_raw[];
+__device__ __forceinline__ Smem& SMEM() { return *reinterpret_cast<Smem*>(fq3_smem_raw); }
+static_assert(sizeof(Smem) <= 232448, "Smem exceeds the 227 KB per-CTA limit");
+
 struct Ctx {
   const KParams& P;
-  Smem& s;
   int tid, warp, lane;
   uint32_t tile_ctr;   // tiles consumed (identical in every consumer thread)
   unsigned bar_target; // thread 0 only
@@ -319,22 +329,22 @@ __device__ __forceinline__ void grid_sync_v4(Ctx& c) {  // last arriver writes o
 __device__ __forceinline__ float block_sum(Ctx& c, float v) {
 #pragma unroll
   for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  if (c.lane == 0) c.s.red[c.warp] = v;
+  if (c.lane == 0) SMEM().red[c.warp] = v;
   csync();
   float r = 0.f;
 #pragma unroll
-  for (int w = 0; w < NCW; ++w) r += c.s.red[w];
+  for (int w = 0; w < NCW; ++w) r += SMEM().red[w];
   csync();
   return r;
 }
 __device__ __forceinline__ float block_max(Ctx& c, float v) {
 #pragma unroll
   for (int o = 16; o; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
-  if (c.lane == 0) c.s.red[c.warp] = v;
+  if (c.lane == 0) SMEM().red[c.warp] = v;
   csync();
-  float r = c.s.red[0];
+  float r = SMEM().red[0];
 #pragma unroll
-  for (int w = 1; w < NCW; ++w) r = fmaxf(r, c.s.red[w]);
+  for (int w = 1; w < NCW; ++w) r = fmaxf(r, SMEM().red[w]);
   csync();
   return r;
 }
@@ -348,6 +358,14 @@ __device__ __forceinline__ void probe(Ctx& c, int& idx) {
   idx++;
 }
 
+__device__ __forceinline__ void probe_at(Ctx& c, int idx) {  // fixed slot (frame-level phases: slots 1024..)
+#ifdef FQ3_NO_FRAME_PROBES
+  return;
+#endif
+  if ((c.P.dbg_on & 2) && blockIdx.x == 0 && c.tid == 0)
+    reinterpret_cast<long long*>(c.P.dbg)[idx] = clock64();
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // GEMV over one segment: rows of this CTA, streamed from the ring.  x: shared memory, NT vectors of stride xstride.
 // Epilogue epi(row0, v0[NT], v1[NT]) is called by lane 0 for each row pair (rows row0, row0+1).
@@ -355,10 +373,10 @@ __device__ __forceinline__ void probe(Ctx& c, int& idx) {
 template <bool BF, int NT, class Epi>
 __device__ __forceinline__ void gemv_seg(Ctx& c, int seg, const float* x, int xstride, Epi epi) {
   constexpr int EPL = BF ? 8 : 4;  // elements per lane per 16-byte load
-  const uint32_t st = c.s.seg[seg];
+  const uint32_t st = SMEM().seg[seg];
   const int gbeg = (int)(st >> 8), gn = (int)(st & 255u);
   for (int gi = 0; gi < gn; ++gi) {
-    const Grp g = c.s.grp[gbeg + gi];
+    const Grp g = SMEM().grp[gbeg + gi];
     const int npairs = g.rows >> 1;
     const int m = g.m;
     float acc[4][NT];
@@ -369,8 +387,8 @@ __device__ __forceinline__ void gemv_seg(Ctx& c, int seg, const float* x, int xs
     for (int tl = 0; tl < g.ntiles; ++tl) {
       const int stage = (int)(c.tile_ctr % NS);
       const uint32_t par = (c.tile_ctr / NS) & 1u;
-      mbar_wait(&c.s.full[stage], par);
-      const uint8_t* tile = c.s.ring[stage];
+      mbar_wait(&SMEM().full[stage], par);
+      const uint8_t* tile = SMEM().ring[stage];
       for (int j = 0; j < m; ++j) {
         const int kb = tl * m + j;
         float xv[NT][EPL];
@@ -411,7 +429,7 @@ __device__ __forceinline__ void gemv_seg(Ctx& c, int seg, const float* x, int xs
         }
       }
       __syncwarp();
-      if (c.lane == 0) mbar_arrive(&c.s.empty[stage]);
+      if (c.lane == 0) mbar_arrive(&SMEM().empty[stage]);
       c.tile_ctr++;
     }
 #pragma unroll
@@ -439,6 +457,18 @@ __device__ __forceinline__ void gemv_seg(Ctx& c, int seg, const float* x, int xs
 // ------------------------------------------------------------------------------------------------------------
 // Producer: stream the segments of the program in consumption order.
 // ------------------------------------------------------------------------------------------------------------
+// ---- split-key talker attention: which cached keys CTA split s of S handles, and how many 64-key ring tiles that is
+constexpr int KVT_KEYS = 64;            // keys per ring tile: K rows at byte 0, V rows at byte KVT_VOFF (bf16, 256 B per row)
+constexpr int KVT_VOFF = STAGE_BYTES / 2;
+constexpr int PART_STRIDE = 132;
+struct KvSlice { int j0, n, ntile; };
+__device__ __forceinline__ KvSlice kv_slice(int nold, int S, int s) {
+  int per = (nold + S - 1) / S;
+  per = (per + 7) & ~7;
+  const int j0 = min(s * per, nold), j1 = min(j0 + per, nold);
+  return KvSlice{j0, j1 - j0, (j1 - j0 + KVT_KEYS - 1) / KVT_KEYS};
+}
+
 struct Producer {
   const KParams& P;
   Smem& s;
@@ -473,9 +503,47 @@ struct Producer {
       }
     }
   }
-  __device__ __forceinline__ void stack_layers(const StackDev& S, int keep_layers = 0) {
+  // K/V rows of this CTA's key slice of layer l -> ring tiles (issued right behind the layer's QKV weights, so they
+  // land while the QKV GEMV and its barrier are still in flight).  Must mirror attention_split().
+  __device__ __forceinline__ void kv_tiles(const StackDev& S, int layer, int slot0, int kv_start) {
+    if (stopped) return;
+    const int Sx = P.attn_split, b = (int)blockIdx.x;
+    if (b >= S.nH * Sx) return;
+    const int h = b / Sx, sp = b - h * Sx, g = h / S.rep;
+    const KvSlice sl = kv_slice(slot0 - kv_start, Sx, sp);
+    const size_t row0 = (size_t)(layer * S.nKV + g) * S.S + kv_start + sl.j0;
+    const uint8_t* kb = reinterpret_cast<const uint8_t*>(S.kc) + row0 * 256;
+    const uint8_t* vb = reinterpret_cast<const uint8_t*>(S.vc) + row0 * 256;
+    for (int tl = 0; tl < sl.ntile; ++tl) {
+      const uint32_t bytes = (uint32_t)min(KVT_KEYS, sl.n - KVT_KEYS * tl) * 256u;
+      const int stage = (int)(ctr % NS);
+      const uint32_t par = ((ctr / NS) & 1u) ^ 1u;
+      while (!mbar_try_wait(&s.empty[stage], par)) {
+        if (s.stop_flag) {
+          stopped = true;
+          return;
+        }
+      }
+      if (s.stop_flag) {
+        stopped = true;
+        return;
+      }
+      mbar_expect_tx(&s.full[stage], 2 * bytes);
+      bulk_g2s(s.ring[stage], kb + (size_t)tl * KVT_KEYS * 256, bytes, &s.full[stage]);
+      bulk_g2s(s.ring[stage] + KVT_VOFF, vb + (size_t)tl * KVT_KEYS * 256, bytes, &s.full[stage]);
+      ++ctr;
+    }
+  }
+  // kv_slot0 >= 0: talker step at cache slot kv_slot0 with split attention
+  __device__ __forceinline__ void stack_layers(const StackDev& S, int keep_layers = 0, int kv_slot0 = -1, int kv_start = 0) {
     for (int l = 0; l < S.L; ++l)
-      for (int q = 0; q < 4; ++q) seg(S.seg_base + 4 * l + q, l < keep_layers);
+      for (int q = 0; q < 4; ++q) {
+        seg(S.seg_base + 4 * l + q, l < keep_layers);
+#ifndef FQ3_NO_SPLIT
+        if (q == 0 && kv_slot0 >= 0 && P.attn_split > 0 && P.mma_tape && kv_slot0 - kv_start >= P.attn_split_min)
+          kv_tiles(S, l, kv_slot0, kv_start);
+#endif
+      }
   }
 };
 
@@ -488,9 +556,9 @@ template <bool BF>
 __device__ void attention_head(Ctx& c, const StackDev& S, int layer, int h, int nt, int slot0, int rpos0,
                                int kv_start) {
   const KParams& P = c.P;
-  float* sc = c.s.xs;                // scores: [nt][scw]
+  float* sc = SMEM().xs;                // scores: [nt][scw]
   const int scw = (nt == 1) ? SEQMAX : 32;
-  float* qs = c.s.xs + SEQMAX;       // [2][128]
+  float* qs = SMEM().xs + SEQMAX;       // [2][128]
   float* ks = qs + 256;              // [2][128]
   float* vs = ks + 256;              // [2][128]
   float* opart = vs + 256;           // [8][128]
@@ -683,6 +751,197 @@ __device__ void attention_head(Ctx& c, const StackDev& S, int layer, int h, int 
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// Talker attention with the keys of every q-head split over P.attn_split CTAs (bf16 engines, one token).
+// CTA b = h * S + s handles q-head h and the s-th slice of the cached keys; the K/V rows of that slice were staged
+// into ring tiles by the producer warp (TMA bulk copies issued behind the QKV weights, i.e. before the barrier that
+// precedes this function), so scores and P.V run out of shared memory.  Each CTA publishes an un-normalised partial
+// (sum_j e^{s_j - m} v_j, m, sum_j e^{s_j - m}); the CTA that arrives last at the head's counter merges the S
+// partials in split order -- deterministic whichever CTA that is -- and writes the head's slice of ATT.
+// Differences to attention_head(): probabilities are not rounded to bf16 before P.V (higher precision, not lower).
+// ------------------------------------------------------------------------------------------------------------
+template <bool BF>
+__device__ void attention_split(Ctx& c, const StackDev& S, int layer, int slot0, int rpos0, int kv_start) {
+  const KParams& P = c.P;
+  const int Sx = P.attn_split, b = (int)blockIdx.x;
+  if (b >= S.nH * Sx) return;  // spare CTAs
+  const int h = b / Sx, sp = b - h * Sx, g = h / S.rep;
+  float* sc = SMEM().xs;           // scores / exponentials of this slice (+ the new key)
+  float* qs = SMEM().xs + 512;     // [128]
+  float* ks = qs + 128;            // [128]
+  float* vs = ks + 128;            // [128]
+  float* opart = vs + 128;         // [8][128]
+  const size_t esz = BF ? 2 : 4;
+  uint8_t* kbase = reinterpret_cast<uint8_t*>(S.kc) + ((size_t)(layer * S.nKV + g) * S.S * 128) * esz;
+  uint8_t* vbase = reinterpret_cast<uint8_t*>(S.vc) + ((size_t)(layer * S.nKV + g) * S.S * 128) * esz;
+  // --- a. q/k norm + rope, v copy: warp 0 q, warp 1 k, warp 2 v; lane owns e, e+32, e+64, e+96
+  if (c.warp < 3) {
+    const int what = c.warp;
+    const float* src = P.QKV + (what == 0 ? h * 128 : (what == 1 ? S.qd + g * 128 : S.qd + S.kd + g * 128));
+    float v[4], nwv[4], cc[4], sv[4];
+    int rp = rpos0;
+    rp = rp < 0 ? 0 : (rp >= S.npos ? S.npos - 1 : rp);
+    const float* cs = S.cos + (size_t)rp * 128;
+    const float* sn = S.sin + (size_t)rp * 128;
+    const void* nw = what == 0 ? S.qnorm : S.knorm;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int e = c.lane + 32 * i;
+      v[i] = __ldcg(src + e);
+      nwv[i] = what < 2 ? ldw<BF>(nw, (size_t)layer * 128 + e) : 0.f;
+      cc[i] = what < 2 ? __ldg(cs + e) : 0.f;
+      sv[i] = what < 2 ? __ldg(sn + e) : 0.f;
+    }
+    if (what < 2) {
+      float ss = v[0] * v[0] + v[1] * v[1] + v[2] * v[2] + v[3] * v[3];
+#pragma unroll
+      for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+      const float r = 1.0f / sqrtf(ss / 128.0f + S.eps);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) v[i] = rnd<BF>(nwv[i] * rnd<BF>(v[i] * r));
+      float o[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float rot = (i < 2) ? -v[i + 2] : v[i - 2];
+        o[i] = rnd<BF>(rnd<BF>(v[i] * rnd<BF>(cc[i])) + rnd<BF>(rot * rnd<BF>(sv[i])));
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) v[i] = o[i];
+    }
+    float* dst = what == 0 ? qs : (what == 1 ? ks : vs);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) dst[c.lane + 32 * i] = v[i];
+    if (what > 0 && sp == 0 && (h % S.rep) == 0) {  // one CTA per kv group appends the new row to the cache
+      uint8_t* cb = (what == 1 ? kbase : vbase) + (size_t)slot0 * 128 * esz;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) stw<BF>(cb, c.lane + 32 * i, v[i]);
+      asm volatile("fence.proxy.async.global;" ::: "memory");  // later steps read these rows through the async proxy (TMA)
+    }
+  }
+  csync();
+  const KvSlice sl = kv_slice(slot0 - kv_start, Sx, sp);
+  const bool has_new = sp == Sx - 1;
+  const int nloc = sl.n + (has_new ? 1 : 0);
+  const float scale = 0.08838834764831845f;  // 128^-0.5
+  const int sub = c.lane & 15, kin = c.lane >> 4;  // 16 lanes per key (16 bytes each), 2 keys per warp instruction
+  // --- b. scores out of the staged K rows
+  {
+    float q[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) q[e] = qs[sub * 8 + e];
+    for (int tl = 0; tl < sl.ntile; ++tl) {
+      const uint32_t tc = c.tile_ctr + (uint32_t)tl;
+      const int stage = (int)(tc % NS);
+      mbar_wait(&SMEM().full[stage], (tc / NS) & 1u);
+      const uint8_t* kt = SMEM().ring[stage];
+      const int n = min(KVT_KEYS, sl.n - KVT_KEYS * tl);
+      for (int j0 = 0; j0 < n; j0 += 2 * NCW) {
+        const int jj = j0 + c.warp * 2 + kin;
+        float d = 0.f;
+        if (jj < n) {
+          const uint4 kv = *reinterpret_cast<const uint4*>(kt + (size_t)jj * 256 + sub * 16);
+          d = fmaf(q[0], bf_lo(kv.x), d); d = fmaf(q[1], bf_hi(kv.x), d);
+          d = fmaf(q[2], bf_lo(kv.y), d); d = fmaf(q[3], bf_hi(kv.y), d);
+          d = fmaf(q[4], bf_lo(kv.z), d); d = fmaf(q[5], bf_hi(kv.z), d);
+          d = fmaf(q[6], bf_lo(kv.w), d); d = fmaf(q[7], bf_hi(kv.w), d);
+        }
+#pragma unroll
+        for (int o = 8; o; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+        if (sub == 0 && jj < n) sc[KVT_KEYS * tl + jj] = rnd<BF>(rnd<BF>(d) * scale);
+      }
+    }
+    if (has_new && c.warp == 0) {
+      float d = 0.f;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) d = fmaf(qs[c.lane + 32 * i], ks[c.lane + 32 * i], d);
+#pragma unroll
+      for (int o = 16; o; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+      if (c.lane == 0) sc[sl.n] = rnd<BF>(rnd<BF>(d) * scale);
+    }
+  }
+  csync();
+  // --- c. slice-local softmax statistics (fp32)
+  float mx = -INFINITY;
+  for (int j = c.tid; j < nloc; j += NCT) mx = fmaxf(mx, sc[j]);
+  mx = block_max(c, mx);
+  float sm = 0.f;
+  for (int j = c.tid; j < nloc; j += NCT) {
+    const float e = expf(sc[j] - mx);
+    sc[j] = e;
+    sm += e;
+  }
+  sm = block_sum(c, sm);
+  // --- d. un-normalised P.V out of the staged V rows
+  {
+    float acc[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+    for (int tl = 0; tl < sl.ntile; ++tl) {
+      const uint32_t tc = c.tile_ctr + (uint32_t)tl;
+      const uint8_t* vt = SMEM().ring[(int)(tc % NS)] + KVT_VOFF;
+      const int n = min(KVT_KEYS, sl.n - KVT_KEYS * tl);
+      for (int j0 = 0; j0 < n; j0 += 2 * NCW) {
+        const int jj = j0 + c.warp * 2 + kin;
+        if (jj < n) {
+          const float pv = sc[KVT_KEYS * tl + jj];
+          const uint4 vv = *reinterpret_cast<const uint4*>(vt + (size_t)jj * 256 + sub * 16);
+          acc[0] = fmaf(pv, bf_lo(vv.x), acc[0]); acc[1] = fmaf(pv, bf_hi(vv.x), acc[1]);
+          acc[2] = fmaf(pv, bf_lo(vv.y), acc[2]); acc[3] = fmaf(pv, bf_hi(vv.y), acc[3]);
+          acc[4] = fmaf(pv, bf_lo(vv.z), acc[4]); acc[5] = fmaf(pv, bf_hi(vv.z), acc[5]);
+          acc[6] = fmaf(pv, bf_lo(vv.w), acc[6]); acc[7] = fmaf(pv, bf_hi(vv.w), acc[7]);
+        }
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], 16);  // fold the two keys of a warp instruction
+    if (has_new && c.warp == 0 && kin == 0) {
+      const float pj = sc[sl.n];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] = fmaf(pj, vs[sub * 8 + e], acc[e]);
+    }
+    if (kin == 0) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) opart[c.warp * 128 + sub * 8 + e] = acc[e];
+    }
+    // hand the ring tiles back to the producer
+    __syncwarp();
+    if (c.lane == 0)
+      for (int tl = 0; tl < sl.ntile; ++tl) mbar_arrive(&SMEM().empty[(int)((c.tile_ctr + (uint32_t)tl) % NS)]);
+    c.tile_ctr += (uint32_t)sl.ntile;
+  }
+  csync();
+  float* part = P.PART + ((size_t)h * Sx + sp) * PART_STRIDE;
+  if (c.tid < 128) {
+    float o = 0.f;
+#pragma unroll
+    for (int w = 0; w < NCW; ++w) o += opart[w * 128 + c.tid];
+    part[c.tid] = o;
+  }
+  if (c.tid == 128) { part[128] = mx; part[129] = sm; }
+  // --- e. arrive at the head's counter; the last split merges
+  csync();
+  if (c.tid == 0) {
+    unsigned old;
+    asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], %2;" : "=r"(old) : "l"(P.attn_cnt + h), "r"(1u) : "memory");
+    SMEM().ibc[0] = ((old + 1u) % (unsigned)Sx) == 0u ? 1 : 0;
+  }
+  csync();
+  if (SMEM().ibc[0] && c.tid < 128) {
+    const float* ph = P.PART + (size_t)h * Sx * PART_STRIDE;
+    float M = -INFINITY;
+    for (int s2 = 0; s2 < Sx; ++s2) M = fmaxf(M, __ldcg(ph + (size_t)s2 * PART_STRIDE + 128));
+    float L = 0.f, o = 0.f;
+    for (int s2 = 0; s2 < Sx; ++s2) {
+      const float m2 = __ldcg(ph + (size_t)s2 * PART_STRIDE + 128);
+      const float w = m2 == -INFINITY ? 0.f : expf(m2 - M);
+      L = fmaf(w, __ldcg(ph + (size_t)s2 * PART_STRIDE + 129), L);
+      o = fmaf(w, __ldcg(ph + (size_t)s2 * PART_STRIDE + c.tid), o);
+    }
+    P.ATT[h * 128 + c.tid] = rnd<BF>(o / L);
+  }
+  csync();
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // Sampling (sampling.py:32-66 + :10-29), computed redundantly and deterministically by every CTA.
 // Returns the token to all consumer threads.
 // ------------------------------------------------------------------------------------------------------------
@@ -707,12 +966,12 @@ __device__ __forceinline__ float fkey_inv(uint32_t k) {
 
 template <bool BF>
 __device__ int sample_block(Ctx& c, const SampleArgs& a) {
-  float* lg = c.s.xs;  // [V]
+  float* lg = SMEM().xs;  // [V]
   const int V = a.V;
   const int sup0 = a.sup0;
   for (int v = c.tid; v < V; v += NCT) {
     float l = __ldcg(a.logits + v);
-    if (a.use_penalty && a.sp.penalty != 1.0f && ((c.s.seen[v >> 5] >> (v & 31)) & 1u))
+    if (a.use_penalty && a.sp.penalty != 1.0f && ((SMEM().seen[v >> 5] >> (v & 31)) & 1u))
       l = l > 0.f ? rnd<BF>(l / a.sp.penalty) : rnd<BF>(l * a.sp.penalty);
     if ((v >= sup0 && v != a.eos) || (a.suppress_eos && v == a.eos)) l = -INFINITY;
     lg[v] = l;
@@ -731,13 +990,13 @@ __device__ int sample_block(Ctx& c, const SampleArgs& a) {
       const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
       if (om > bm || (om == bm && oi < bi)) { bm = om; bi = oi; }
     }
-    if (c.lane == 0) { c.s.red[c.warp] = bm; c.s.hist[c.warp] = bi; }
+    if (c.lane == 0) { SMEM().red[c.warp] = bm; SMEM().hist[c.warp] = bi; }
     csync();
-    float m = c.s.red[0];
-    int bi2 = c.s.hist[0];
+    float m = SMEM().red[0];
+    int bi2 = SMEM().hist[0];
     for (int w = 1; w < NCW; ++w) {
-      const float om = c.s.red[w];
-      const int oi = c.s.hist[w];
+      const float om = SMEM().red[w];
+      const int oi = SMEM().hist[w];
       if (om > m || (om == m && oi < bi2)) { m = om; bi2 = oi; }
     }
     csync();
@@ -752,17 +1011,17 @@ __device__ int sample_block(Ctx& c, const SampleArgs& a) {
     int remaining = a.sp.top_k;
     for (int pass = 0; pass < (BF ? 2 : 4); ++pass) {  // bf16-rounded logits have 16 zero low bits
       const int shift = 24 - 8 * pass;
-      c.s.hist[c.tid] = 0;
+      SMEM().hist[c.tid] = 0;
       csync();
       for (int v = c.tid; v < V; v += NCT) {
         const uint32_t k = fkey(lg[v]);
-        if ((k & mask) == prefix) atomicAdd(&c.s.hist[(k >> shift) & 255u], 1);
+        if ((k & mask) == prefix) atomicAdd(&SMEM().hist[(k >> shift) & 255u], 1);
       }
       csync();
       if (c.warp == 0) {  // lane L owns bins 255-8L .. 248-8L (descending)
         int cnt[8], tot = 0;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { cnt[i] = c.s.hist[255 - 8 * c.lane - i]; tot += cnt[i]; }
+        for (int i = 0; i < 8; ++i) { cnt[i] = SMEM().hist[255 - 8 * c.lane - i]; tot += cnt[i]; }
         int incl = tot;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -775,17 +1034,17 @@ __device__ int sample_block(Ctx& c, const SampleArgs& a) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             if (run < remaining && run + cnt[i] >= remaining) {
-              c.s.ibc[0] = 255 - 8 * c.lane - i;
-              c.s.ibc[1] = remaining - run;
+              SMEM().ibc[0] = 255 - 8 * c.lane - i;
+              SMEM().ibc[1] = remaining - run;
             }
             run += cnt[i];
           }
         }
       }
       csync();
-      prefix |= ((uint32_t)c.s.ibc[0]) << shift;
+      prefix |= ((uint32_t)SMEM().ibc[0]) << shift;
       mask |= 255u << shift;
-      remaining = c.s.ibc[1];
+      remaining = SMEM().ibc[1];
       csync();
     }
     const float kth = fkey_inv(prefix);
@@ -795,8 +1054,8 @@ __device__ int sample_block(Ctx& c, const SampleArgs& a) {
   }
   // top-p (fp32 semantics, order: value desc then index asc; keep position 0 and every position with cum <= top_p)
   if (a.sp.top_p < 1.0f) {
-    float* sl = &c.s.xin[0][0];                                      // sorted values [V] (xin is free here)
-    uint16_t* rk = reinterpret_cast<uint16_t*>(c.s.xs + VMAX);       // ranks [V]
+    float* sl = &SMEM().xin[0][0];                                      // sorted values [V] (xin is free here)
+    uint16_t* rk = reinterpret_cast<uint16_t*>(SMEM().xs + VMAX);       // ranks [V]
     for (int v = c.tid; v < V; v += NCT) {
       const float l = lg[v];
       int r = 0;
@@ -819,10 +1078,10 @@ __device__ int sample_block(Ctx& c, const SampleArgs& a) {
         if (i > 0 && !(cum > a.sp.top_p)) keep = i + 1;
         if (cum > a.sp.top_p && i > 0) break;
       }
-      c.s.ibc[2] = keep;
+      SMEM().ibc[2] = keep;
     }
     csync();
-    const int keep = c.s.ibc[2];
+    const int keep = SMEM().ibc[2];
     for (int v = c.tid; v < V; v += NCT)
       if ((int)rk[v] >= keep) lg[v] = -INFINITY;
     csync();
@@ -853,16 +1112,16 @@ __device__ int sample_block(Ctx& c, const SampleArgs& a) {
     const float n = __shfl_up_sync(0xffffffffu, incl, o);
     if (c.lane >= o) incl += n;
   }
-  if (c.lane == 31) c.s.red[c.warp] = incl;
+  if (c.lane == 31) SMEM().red[c.warp] = incl;
   if (c.tid == 0) {
-    c.s.ibc[3] = -1;
-    c.s.ibc[0] = 0x7fffffff;
+    SMEM().ibc[3] = -1;
+    SMEM().ibc[0] = 0x7fffffff;
   }
   csync();
   float woff = 0.f, total = 0.f;
   for (int w = 0; w < NCW; ++w) {
     if (w == c.warp) woff = total;
-    total += c.s.red[w];
+    total += SMEM().red[w];
   }
   incl += woff;
   const float target = a.u * total;
@@ -871,9 +1130,9 @@ __device__ int sample_block(Ctx& c, const SampleArgs& a) {
   // lowest chunk whose inclusive prefix exceeds the target (prefix sums need not be monotone in fp32; the
   // oracle takes the first such chunk too)
   const bool hit = incl > target;
-  if (hit) atomicMin(&c.s.ibc[0], c.tid);
+  if (hit) atomicMin(&SMEM().ibc[0], c.tid);
   csync();
-  if (hit && c.s.ibc[0] == c.tid) {
+  if (hit && SMEM().ibc[0] == c.tid) {
     float run = excl;
     int pick = -1;
     for (int j = 0; j < CH; ++j) {
@@ -882,20 +1141,20 @@ __device__ int sample_block(Ctx& c, const SampleArgs& a) {
       run += lg[idx];
       if (run > target && lg[idx] > 0.f) { pick = idx; break; }
     }
-    c.s.ibc[3] = pick;
+    SMEM().ibc[3] = pick;
   }
   csync();
-  int tok = c.s.ibc[3];
+  int tok = SMEM().ibc[3];
   if (tok < 0) {  // rounding left nothing selected: last index with p > 0
     int best = -1;
     for (int v = c.tid; v < V; v += NCT)
       if (lg[v] > 0.f) best = v > best ? v : best;
 #pragma unroll
     for (int o = 16; o; o >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, o));
-    if (c.lane == 0) c.s.hist[c.warp] = best;
+    if (c.lane == 0) SMEM().hist[c.warp] = best;
     csync();
-    tok = c.s.hist[0];
-    for (int w = 1; w < NCW; ++w) tok = max(tok, c.s.hist[w]);
+    tok = SMEM().hist[0];
+    for (int w = 1; w < NCW; ++w) tok = max(tok, SMEM().hist[w]);
     if (tok < 0) tok = 0;
   }
   csync();
@@ -920,13 +1179,13 @@ __device__ __forceinline__ void mma_bf16(float* d, const uint4& a, uint32_t b0, 
 
 template <int NT, class Pre, class Epi>
 __device__ __forceinline__ void gemv_mma(Ctx& c, int seg, int K, Pre pre, Epi epi) {
-  const __nv_bfloat16* xh = reinterpret_cast<const __nv_bfloat16*>(c.s.xs);
-  float* red = c.s.xs + XS_FLOATS / 2;  // [NCW][2][4][32] partial accumulators
-  const uint32_t st = c.s.seg[seg];
+  const __nv_bfloat16* xh = reinterpret_cast<const __nv_bfloat16*>(SMEM().xs);
+  float* red = SMEM().xs + XS_FLOATS / 2;  // [NCW][2][4][32] partial accumulators
+  const uint32_t st = SMEM().seg[seg];
   const int gbeg = (int)(st >> 8), gn = (int)(st & 255u);
   const int gq = c.lane >> 2, t = c.lane & 3;
   for (int gi = 0; gi < gn; ++gi) {
-    const Grp g = c.s.grp[gbeg + gi];
+    const Grp g = SMEM().grp[gbeg + gi];
     const int n_mt = g.rows & 0xff, kind = g.rows >> 8, G = g.m;
     int tok, koff;
     bool bvalid;
@@ -951,8 +1210,8 @@ __device__ __forceinline__ void gemv_mma(Ctx& c, int seg, int K, Pre pre, Epi ep
     for (int tl = 0; tl < g.ntiles; ++tl) {
       const int stage = (int)(c.tile_ctr % NS);
       const uint32_t par = (c.tile_ctr / NS) & 1u;
-      mbar_wait(&c.s.full[stage], par);
-      const uint8_t* tile = c.s.ring[stage];
+      mbar_wait(&SMEM().full[stage], par);
+      const uint8_t* tile = SMEM().ring[stage];
       for (int qq = c.warp; qq < G; qq += NCW) {
         const int kg = tl * G + qq;
         uint4 blo = make_uint4(0, 0, 0, 0), bhi = make_uint4(0, 0, 0, 0);
@@ -973,7 +1232,7 @@ __device__ __forceinline__ void gemv_mma(Ctx& c, int seg, int K, Pre pre, Epi ep
         }
       }
       __syncwarp();
-      if (c.lane == 0) mbar_arrive(&c.s.empty[stage]);
+      if (c.lane == 0) mbar_arrive(&SMEM().empty[stage]);
       c.tile_ctr++;
     }
 #pragma unroll
@@ -1025,21 +1284,21 @@ __device__ __forceinline__ void gemv_any(Ctx& c, int seg, int nt, int K, Pre pre
         }
       }
     };
-    if (nt == 1) gemv_seg<false, 1>(c, seg, c.s.xs, K, epi2);
-    else gemv_seg<false, 2>(c, seg, c.s.xs, K, epi2);
+    if (nt == 1) gemv_seg<false, 1>(c, seg, SMEM().xs, K, epi2);
+    else gemv_seg<false, 2>(c, seg, SMEM().xs, K, epi2);
   }
 }
 
 // staging vector element store: bf16 array (tensor-core path) or fp32 array (fp32 parity mode), both in s.xs
 template <bool BF>
 __device__ __forceinline__ void xs_put(Ctx& c, int idx, float v) {
-  if constexpr (BF) reinterpret_cast<__nv_bfloat16*>(c.s.xs)[idx] = __float2bfloat16_rn(v);
-  else c.s.xs[idx] = v;
+  if constexpr (BF) reinterpret_cast<__nv_bfloat16*>(SMEM().xs)[idx] = __float2bfloat16_rn(v);
+  else SMEM().xs[idx] = v;
 }
 template <bool BF>
 __device__ __forceinline__ float xs_get(Ctx& c, int idx) {
-  if constexpr (BF) return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(c.s.xs)[idx]);
-  else return c.s.xs[idx];
+  if constexpr (BF) return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(SMEM().xs)[idx]);
+  else return SMEM().xs[idx];
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -1308,9 +1567,13 @@ __device__ __forceinline__ void norm_stage(Ctx& c, const float* src, bool src_sm
 // On return every CTA holds the final-norm hidden of the LAST token in the staging vector [0..H) and X holds the
 // residual stream.
 // ------------------------------------------------------------------------------------------------------------
-template <bool BF>
-__device__ void run_layers(Ctx& c, const StackDev& S, int nt, int slot0, int rpos0, int kv_start, bool x0_local,
-                           bool dbg, bool is_talker) {
+// TALKER selects, at compile time, which attention the instantiation contains: the talker's (one q-head per CTA, or
+// keys split over several CTAs with TMA-staged K/V) or the predictor's (every CTA computes all heads of the <= 17-key
+// cache redundantly).  Two separate real functions: changing one attention cannot perturb the code of the other pass.
+template <bool BF, bool TALKER>
+__device__ void run_layers(Ctx& c, const StackDev& S, int nt, int slot0, int rpos0, int kv_start,
+                                        bool x0_local, bool dbg) {
+  constexpr bool is_talker = TALKER;
   const KParams& P = c.P;
   const bool cta0 = blockIdx.x == 0;
   int pi = 0;
@@ -1322,14 +1585,14 @@ __device__ void run_layers(Ctx& c, const StackDev& S, int nt, int slot0, int rpo
     // ---- P1: input norm + QKV rows
     for (int t = 0; t < nt; ++t) {
       const float* wp = l > 0 ? wnext : nullptr;
-      if (l == 0 && x0_local) norm_stage<BF>(c, c.s.xin[t], true, S.ln_in, (size_t)l * S.H, S.H, S.eps, t * S.H, wp);
+      if (l == 0 && x0_local) norm_stage<BF>(c, SMEM().xin[t], true, S.ln_in, (size_t)l * S.H, S.H, S.eps, t * S.H, wp);
       else norm_stage<BF>(c, P.X + (size_t)t * P.ldX, false, S.ln_in, (size_t)l * S.H, S.H, S.eps, t * S.H, wp);
     }
     probe(c, pi);  // 1: after input norm
     gemv_any<BF, false>(c, S.seg_base + 4 * l + 0, nt, S.H, nopre,
                         [&](int row, int t, float v, float, float) { P.QKV[(size_t)t * P.ldQKV + row] = rnd<BF>(v); });
     probe(c, pi);  // 2: after QKV gemv
-    const bool small_attn = !is_talker && S.S <= 32 && S.rep <= 2 && ((nt == 1 && slot0 <= 16) || (nt == 2 && slot0 == 0));
+    const bool small_attn = !TALKER;   // geometry checked by fq3_engine_create (cache <= 32 slots, <= 2 q-heads per kv head)
     const bool kv_pre = small_attn && nt == 1 && S.nKV <= NCW;
     SmallKV<BF> skv;
     grid_arrive(c);
@@ -1341,16 +1604,24 @@ __device__ void run_layers(Ctx& c, const StackDev& S, int nt, int slot0, int rpo
       for (int t = 0; t < nt; ++t)
         for (int k = c.tid; k < S.qd + 2 * S.kd; k += NCT) d[(size_t)t * (S.qd + 2 * S.kd) + k] = __ldcg(P.QKV + (size_t)t * P.ldQKV + k);
     }
-    if (small_attn) {
+    if constexpr (!TALKER) {
       // ---- P2+P3 fused: redundant small attention straight into the staging vector (no exchange, no barrier)
       if (nt == 1) attention_small_all<BF, 1>(c, S, l, slot0, rpos0, kv_pre ? &skv : nullptr);
       else attention_small_all<BF, 2>(c, S, l, slot0, rpos0);
       probe(c, pi);  // 4
       probe(c, pi);  // 5
     } else {
-      // ---- P2: attention, one q-head per CTA
-      for (int h = blockIdx.x; h < S.nH; h += gridDim.x) attention_head<BF>(c, S, l, h, nt, slot0, rpos0, kv_start);
-      if (is_talker && (int)blockIdx.x >= S.nH && slot0 - kv_start > 64) {
+      // ---- P2: attention.  bf16 talker steps: keys split over attn_split CTAs per q-head, K/V slices TMA-staged;
+      //          otherwise one q-head per CTA reading the cache directly
+#ifdef FQ3_NO_SPLIT
+      const bool split = false;
+#else
+      const bool split = BF && is_talker && nt == 1 && P.attn_split > 0 && slot0 - kv_start >= P.attn_split_min;
+#endif
+      if (split) attention_split<BF>(c, S, l, slot0, rpos0, kv_start);
+      else
+        for (int h = blockIdx.x; h < S.nH; h += gridDim.x) attention_head<BF>(c, S, l, h, nt, slot0, rpos0, kv_start);
+      if (!split && is_talker && (int)blockIdx.x >= S.nH && slot0 - kv_start > 64) {
         // idle CTAs pull the NEXT layer's keys/values into L2 (evict_last) so the attention CTAs see L2 latency
         const int ln = (l + 1) % S.L;
         const size_t esz = BF ? 2 : 4;
@@ -1386,7 +1657,7 @@ __device__ void run_layers(Ctx& c, const StackDev& S, int nt, int slot0, int rpo
       const bool loc = (l == 0 && x0_local);
       gemv_any<BF, false>(
           c, S.seg_base + 4 * l + 1, nt, S.qd,
-          [&](int row, int t) { return loc ? c.s.xin[t][row] : __ldcg(P.X + (size_t)t * P.ldX + row); },
+          [&](int row, int t) { return loc ? SMEM().xin[t][row] : __ldcg(P.X + (size_t)t * P.ldX + row); },
           [&](int row, int t, float v, float, float res) { P.X1[(size_t)t * P.ldX + row] = rnd<BF>(res + rnd<BF>(v)); });
     }
     probe(c, pi);  // 6: after O gemv
@@ -1456,16 +1727,23 @@ __device__ void predictor_frame(Ctx& c, const float* u15, bool dbg) {
   const int Ht = P.t.H;
   for (int i = 0; i < P.ncb; ++i) {
     const int nt = (i == 0) ? 2 : 1;
+    probe_at(c, 1024 + 8 * i + 0);
+    const bool tabled = i > 0 && P.has_mtp && P.mtp_tab != nullptr;
     if (i > 0) {
-      const int prev = c.s.codes[i];  // code sampled by pass i-1
-      for (int k = c.tid; k < Ht; k += NCT)
-        c.s.xin[0][k] = ldw<BF>(P.p_embeds, ((size_t)(i - 1) * S.V + prev) * Ht + k);
+      const int prev = SMEM().codes[i];  // code sampled by pass i-1
+      if (tabled) {  // small_to_mtp_projection(codec_embedding[i-1](prev)) was tabulated when the weights were loaded
+        for (int k = c.tid; k < S.H; k += NCT)
+          SMEM().xin[0][k] = ldw<BF>(P.mtp_tab, ((size_t)(i - 1) * S.V + prev) * S.H + k);
+      } else {
+        for (int k = c.tid; k < Ht; k += NCT)
+          SMEM().xin[0][k] = ldw<BF>(P.p_embeds, ((size_t)(i - 1) * S.V + prev) * Ht + k);
+      }
       csync();
     }
     bool x0_local;
-    if (P.has_mtp) {
+    if (P.has_mtp && !tabled) {
       for (int t = 0; t < nt; ++t)
-        for (int k = c.tid; k < Ht; k += NCT) xs_put<BF>(c, t * Ht + k, c.s.xin[t][k]);
+        for (int k = c.tid; k < Ht; k += NCT) xs_put<BF>(c, t * Ht + k, SMEM().xin[t][k]);
       csync();
       gemv_any<BF, false>(c, P.seg_mtp, nt, Ht, [&](int row, int) { return P.mtp_b ? ldw<BF>(P.mtp_b, row) : 0.f; },
                           [&](int row, int t, float v, float, float b) { P.X[(size_t)t * P.ldX + row] = rnd<BF>(v + b); });
@@ -1475,15 +1753,53 @@ __device__ void predictor_frame(Ctx& c, const float* u15, bool dbg) {
       x0_local = true;
     }
     const int slot0 = (i == 0) ? 0 : i + 1;
-    run_layers<BF>(c, S, nt, slot0, slot0, 0, x0_local, dbg && i == 0, false);
+    probe_at(c, 1024 + 8 * i + 1);
+    run_layers<BF, false>(c, S, nt, slot0, slot0, 0, x0_local, dbg && i == 0);
+    probe_at(c, 1024 + 8 * i + 2);
     head_logits<BF>(c, S.seg_head + i, S.H);
+    probe_at(c, 1024 + 8 * i + 3);
     SampleArgs sa;
     sa.logits = P.LOGITS; sa.V = S.V; sa.sp = P.sp_p; sa.u = u15 ? __ldg(u15 + i) : 0.f;
     sa.use_penalty = false; sa.sup0 = S.V; sa.suppress_eos = false; sa.eos = -1;
     const int tok = sample_block<BF>(c, sa);
-    if (c.tid == 0) c.s.codes[i + 1] = tok;
+    if (c.tid == 0) SMEM().codes[i + 1] = tok;
     csync();
+    probe_at(c, 1024 + 8 * i + 4);
   }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// The producer warp's whole life, as one real function: its code generation (counters in registers, no spills) must
+// not depend on how much register pressure the consumer code around it creates -- a slow producer slows every phase.
+// ------------------------------------------------------------------------------------------------------------
+__device__ __noinline__ void producer_main(const KParams& P) {
+  Smem& s = SMEM();
+  const int lane = (int)(threadIdx.x & 31u);
+    if (lane == 0) {
+      Producer pr{P, s, 0u, false, 0ull, 0ull};
+      asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pr.pol_first));
+      asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pr.pol_last));
+      if (P.mode == MODE_BARRIER_TEST) {
+      } else if (P.mode == MODE_TALKER_STEP) {
+        pr.stack_layers(P.t, 0, P.position, P.n_left_pad);
+      } else {
+        const int iters = P.mode == MODE_FUSED ? P.n_frames : 1;
+        for (int f = 0; f < iters && !pr.stopped; ++f) {
+          for (int i = 0; i < P.ncb; ++i) {
+            if (P.has_mtp && (i == 0 || P.mtp_tab == nullptr)) pr.seg(P.seg_mtp, true);
+            pr.stack_layers(P.p, P.pred_pin_layers);
+            pr.seg(P.p.seg_head + i);
+          }
+          if (P.mode == MODE_FUSED) {
+            pr.stack_layers(P.t, 0, P.prefill_len + P.state[1] + f, P.n_left_pad);
+            pr.seg(P.t.seg_head);
+          }
+        }
+      }
+      s.prod_issued = (int)pr.ctr;
+      __threadfence_block();
+      s.prod_done = 1;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -1517,35 +1833,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) fq3_decode_kernel(const __grid_co
   __syncthreads();
 
   if (warp == NCW) {
-    // ======================================= PRODUCER =======================================
-    if (lane == 0) {
-      Producer pr{P, s, 0u, false, 0ull, 0ull};
-      asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pr.pol_first));
-      asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pr.pol_last));
-      if (P.mode == MODE_BARRIER_TEST) {
-      } else if (P.mode == MODE_TALKER_STEP) {
-        pr.stack_layers(P.t);
-      } else {
-        const int iters = P.mode == MODE_FUSED ? P.n_frames : 1;
-        for (int f = 0; f < iters && !pr.stopped; ++f) {
-          for (int i = 0; i < P.ncb; ++i) {
-            if (P.has_mtp) pr.seg(P.seg_mtp, true);
-            pr.stack_layers(P.p, P.pred_pin_layers);
-            pr.seg(P.p.seg_head + i);
-          }
-          if (P.mode == MODE_FUSED) {
-            pr.stack_layers(P.t);
-            pr.seg(P.t.seg_head);
-          }
-        }
-      }
-      s.prod_issued = (int)pr.ctr;
-      __threadfence_block();
-      s.prod_done = 1;
-    }
+    producer_main(P);
   } else {
     // ======================================= CONSUMERS ======================================
-    Ctx c{P, s, tid, warp, lane, 0u, 0u};
+    Ctx c{P, tid, warp, lane, 0u, 0u};
     const int Ht = P.t.H;
     if (P.mode == MODE_BARRIER_TEST) {
       for (int i = 0; i < P.n_frames; ++i) {
@@ -1558,7 +1849,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fq3_decode_kernel(const __grid_co
     } else if (P.mode == MODE_TALKER_STEP) {
       for (int k = tid; k < Ht; k += NCT) s.xin[0][k] = ldw<BF>(P.in_embeds, k);
       csync();
-      run_layers<BF>(c, P.t, 1, P.position, P.position + P.rope_delta, P.n_left_pad, true, P.dbg_on != 0, true);
+      run_layers<BF, true>(c, P.t, 1, P.position, P.position + P.rope_delta, P.n_left_pad, true, P.dbg_on != 0);
       if (cta == 0)
         for (int k = tid; k < Ht; k += NCT) stw<BF>(P.hidden_out, k, xs_get<BF>(c, k));
     } else if (P.mode == MODE_PRED_RUN) {
@@ -1587,7 +1878,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) fq3_decode_kernel(const __grid_co
         }
         csync();
         const float* urow = P.uniforms + (size_t)(step + 1) * 16;
+        const int pslot = 2048 + 8 * (emitted & 63);
+        probe_at(c, pslot + 0);
         predictor_frame<BF>(c, P.sp_p.do_sample ? urow + 1 : nullptr, false);
+        probe_at(c, pslot + 1);
         if (cta == 0 && tid < 16) P.codes_out[(size_t)emitted * 16 + tid] = (long long)s.codes[tid];
         emitted++;
         // next talker input: sum of 16 embedding rows + trailing text / tts_pad   generate.py:163-171
@@ -1603,15 +1897,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) fq3_decode_kernel(const __grid_co
         }
         const int pos = P.prefill_len + step;
         if (pos >= P.max_seq_len - 1) { finished = 3; step++; break; }   // generate.py:175-177 (frame already emitted)
-        run_layers<BF>(c, P.t, 1, pos, pos + P.rope_delta, P.n_left_pad, true, false, true);
+        probe_at(c, pslot + 2);
+        run_layers<BF, true>(c, P.t, 1, pos, pos + P.rope_delta, P.n_left_pad, true, false);
+        probe_at(c, pslot + 3);
         for (int k = tid; k < Ht; k += NCT) s.hid[k] = xs_get<BF>(c, k);   // past_hidden = post-norm hidden (generate.py:198)
         csync();
         head_logits<BF>(c, P.t.seg_head, Ht);
+        probe_at(c, pslot + 4);
         SampleArgs sa;
         sa.logits = P.LOGITS; sa.V = P.t.V; sa.sp = P.sp_t; sa.u = P.sp_t.do_sample ? __ldg(urow) : 0.f;
         sa.use_penalty = true; sa.sup0 = P.t.V > 1024 ? P.t.V - 1024 : 0;
         sa.suppress_eos = (step + 1) < P.min_new; sa.eos = P.eos;
         token = sample_block<BF>(c, sa);
+        probe_at(c, pslot + 5);
         step++;
         gen_step++;
       }

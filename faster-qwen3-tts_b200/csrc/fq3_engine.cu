@@ -55,7 +55,7 @@ struct fq3_engine {
   bool request_active = false;
   // device buffers
   void *t_kc = nullptr, *t_vc = nullptr, *p_kc = nullptr, *p_vc = nullptr;
-  float *X = nullptr, *X1 = nullptr, *QKV = nullptr, *ATT = nullptr, *ACT = nullptr, *LOGITS = nullptr;
+  float *X = nullptr, *X1 = nullptr, *QKV = nullptr, *ATT = nullptr, *ACT = nullptr, *LOGITS = nullptr, *PART = nullptr;
   unsigned* bar = nullptr;
   int* state = nullptr;
   int* state_host = nullptr;  // pinned
@@ -195,7 +195,7 @@ __global__ void __launch_bounds__(NCT, 1)
   for (int v = tid; v < V; v += NCT) P.LOGITS[v] = ldw<BF>(logits, v);
   __threadfence();
   __syncthreads();
-  Ctx c{P, s, tid, tid >> 5, tid & 31, 0u, 0u};
+  Ctx c{P, tid, tid >> 5, tid & 31, 0u, 0u};
   SampleArgs a;
   a.logits = P.LOGITS; a.V = V; a.sp = sp; a.u = u;
   a.use_penalty = true;
@@ -276,6 +276,7 @@ extern "C" int fq3_engine_create(const fq3_config* cfg, fq3_engine** out) {
   CK(cudaMalloc(&e->QKV, 2 * ldQKV * sizeof(float))); CK(cudaMalloc(&e->ATT, 2 * ldATT * sizeof(float)));
   CK(cudaMalloc(&e->ACT, 2 * ldACT * sizeof(float))); CK(cudaMalloc(&e->LOGITS, VMAX * sizeof(float)));
   CK(cudaMalloc(&e->bar, 32768)); CK(cudaMemset(e->bar, 0, 32768));
+  CK(cudaMalloc(&e->PART, (size_t)T.num_attention_heads * 16 * PART_STRIDE * sizeof(float)));
   CK(cudaMalloc(&e->state, 64)); CK(cudaMemset(e->state, 0, 64));
   CK(cudaMallocHost(&e->state_host, 64));
   CK(cudaMalloc(&e->past_hidden, HMAX * sizeof(float))); CK(cudaMemset(e->past_hidden, 0, HMAX * sizeof(float)));
@@ -306,6 +307,17 @@ extern "C" int fq3_engine_create(const fq3_config* cfg, fq3_engine** out) {
   k.max_seq_len = cfg->max_seq_len;
   k.dbg = e->dbg; k.dbg_stride_layer = e->dbg_stride;
   k.pred_pin_layers = 2;
+  {
+    // split-key talker attention (bf16 engines): S CTAs per q-head; a slice must fit the 4 ring tiles it may hold
+    int Sx = e->bf16 ? std::min(e->ncta / std::max(T.num_attention_heads, 1), 16) : 0;
+    if (Sx < 2 || (cfg->max_seq_len + Sx - 1) / Sx > 4 * KVT_KEYS) Sx = 0;
+    if (const char* v = getenv("FQ3_ATTN_SPLIT")) Sx = std::min(Sx, std::max(atoi(v), 0)) < 2 ? 0 : std::min(Sx, atoi(v));
+    k.attn_split = Sx;
+    k.attn_split_min = 448;   // measured crossover on B200 (1.7B geometry): per-head CTAs win below ~450 cached keys
+    if (const char* v = getenv("FQ3_ATTN_SPLIT_MIN")) k.attn_split_min = std::max(atoi(v), 0);
+    k.PART = e->PART;
+    k.attn_cnt = e->bar + 1024;
+  }
   k.sp_t = Sampling{1, 50, 0.9f, 1.0f, 1.05f};
   k.sp_p = Sampling{1, 50, 0.9f, 1.0f, 1.0f};
   *out = e;
@@ -315,7 +327,7 @@ extern "C" int fq3_engine_create(const fq3_config* cfg, fq3_engine** out) {
 extern "C" void fq3_engine_destroy(fq3_engine* e) {
   if (!e) return;
   cudaSetDevice(e->dev);
-  void* ptrs[] = {e->t_kc, e->t_vc, e->p_kc, e->p_vc, e->X, e->X1, e->QKV, e->ATT, e->ACT, e->LOGITS, e->bar,
+  void* ptrs[] = {e->t_kc, e->t_vc, e->p_kc, e->p_vc, e->X, e->X1, e->QKV, e->ATT, e->ACT, e->LOGITS, e->PART, e->bar,
                   e->state, e->past_hidden, e->seen, e->dbg, e->tape, e->grps, e->segtab, e->cta_grp_off};
   for (void* p : ptrs)
     if (p) cudaFree(p);
@@ -325,6 +337,40 @@ extern "C" void fq3_engine_destroy(fq3_engine* e) {
     if (p) cudaFree(p);
   if (e->state_host) cudaFreeHost(e->state_host);
   delete e;
+}
+
+// table[r][o] = round(bias[o] + sum_k W[o][k] * emb[r][k]) for every row r of the 15 predictor codec embeddings:
+// the code predictor's input projection (predictor_graph.py:53 small_to_mtp_projection) of an embedding row depends
+// only on the code, so it is tabulated once per weight load instead of being recomputed (GEMV + grid barrier) in 14
+// of the 15 passes of every frame.  4 embedding rows per block, one warp per output row.
+template <bool BF>
+__global__ void mtp_table_kernel(const void* __restrict__ emb, const void* __restrict__ W, const void* __restrict__ bias,
+                                 void* __restrict__ table, int K, int N, long long rows) {
+  extern __shared__ float es[];  // [4][K]
+  const long long r0 = (long long)blockIdx.x * 4;
+  for (int i = threadIdx.x; i < 4 * K; i += blockDim.x) {
+    const long long r = r0 + i / K;
+    es[i] = r < rows ? ldw<BF>(emb, (size_t)r * K + (i % K)) : 0.f;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int o = warp; o < N; o += nw) {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int k = lane; k < K; k += 32) {
+      const float w = ldw<BF>(W, (size_t)o * K + k);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[j] = fmaf(w, es[j * K + k], acc[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int s = 16; s; s >>= 1) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], s);
+    if (lane < 4 && r0 + lane < rows) {
+      const float b = bias ? ldw<BF>(bias, o) : 0.f;
+      const float v = lane == 0 ? acc[0] : (lane == 1 ? acc[1] : (lane == 2 ? acc[2] : acc[3]));
+      stw<BF>(table, (size_t)(r0 + lane) * N + o, rnd<BF>(v + b));
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -383,8 +429,27 @@ extern "C" int fq3_engine_load_weights(fq3_engine* e, const fq3_tensor* tensors,
     const int Ht = cfg.talker.hidden_size;
     if ((rc = own("t.embed", (int64_t)cfg.talker.vocab_size * Ht, esz, &k.t_embed))) return rc;
     if ((rc = own("p.embeds", (int64_t)k.ncb * cfg.predictor.vocab_size * Ht, esz, &k.p_embeds))) return rc;
+    k.mtp_tab = nullptr;
     if (cfg.has_mtp_projection) {
       if ((rc = own("p.mtp_b", cfg.predictor.hidden_size, esz, &k.mtp_b))) return rc;
+      const char* off = getenv("FQ3_NO_MTP_TABLE");
+      const size_t sm = (size_t)4 * Ht * sizeof(float);
+      if (!(off && off[0] == '1') && sm <= 48 * 1024) {
+        const void* wm;
+        const int Hp = cfg.predictor.hidden_size;
+        if ((rc = need("p.mtp_w", (int64_t)Hp * Ht, &wm))) return rc;
+        const long long rows = (long long)k.ncb * cfg.predictor.vocab_size;
+        void* tab = nullptr;
+        auto it = e->tabs.find("p.mtp_table");
+        if (it != e->tabs.end() && it->second) cudaFree(it->second);
+        CK(cudaMalloc(&tab, (size_t)rows * Hp * esz));
+        e->tabs["p.mtp_table"] = tab;
+        const unsigned nb = (unsigned)((rows + 3) / 4);
+        if (e->bf16) mtp_table_kernel<true><<<nb, 256, sm, stream>>>(k.p_embeds, wm, k.mtp_b, tab, Ht, Hp, rows);
+        else mtp_table_kernel<false><<<nb, 256, sm, stream>>>(k.p_embeds, wm, k.mtp_b, tab, Ht, Hp, rows);
+        CK(cudaGetLastError());
+        k.mtp_tab = tab;
+      }
     } else {
       k.mtp_b = nullptr;
     }
@@ -628,7 +693,7 @@ extern "C" int fq3_engine_load_weights(fq3_engine* e, const fq3_tensor* tensors,
     for (int i = 0; i < k.ncb; ++i) ph += segs[k.p.seg_head + i].bytes;
     if (k.seg_mtp >= 0) pm = segs[k.seg_mtp].bytes;
     e->talker_step_bytes = (int64_t)tl;
-    e->predictor_frame_bytes = (int64_t)(k.ncb * (pl + pm) + ph);
+    e->predictor_frame_bytes = (int64_t)(k.ncb * pl + (k.mtp_tab ? 1 : k.ncb) * pm + ph);
   }
   e->loaded = true;
   return 0;
@@ -758,7 +823,7 @@ extern "C" int fq3_decode_chunk(fq3_engine* e, int32_t n_frames, int64_t* codes_
   kp.mode = MODE_FUSED;
   kp.n_frames = n_frames;
   kp.codes_out = (long long*)codes_out_dev;
-  kp.dbg_on = 0;
+  kp.dbg_on = e->dbg_on & 2;   // timing probes only; layer dumps belong to the step-wise entry points
   int rc = launch_decode(e, kp, stream);
   if (rc) return rc;
   CK(cudaMemcpyAsync(e->state_host, e->state, 32, cudaMemcpyDeviceToHost, stream));

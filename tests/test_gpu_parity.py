@@ -328,3 +328,36 @@ def test_public_api_end_to_end_tiny():
     assert a[0].shape[0] == 9 * 1920
     with pytest.raises(ValueError, match="ref_audio is required"):
         m.generate_voice_clone("x", "English")
+
+
+@pytest.mark.gpu
+def test_split_attention_matches_per_head_attention(monkeypatch):
+    """bf16 talker steps: keys split over several CTAs per q-head with TMA-staged K/V slices (default) against one
+    CTA per q-head reading the cache directly (FQ3_ATTN_SPLIT=0): same weights, same imported cache, positions that
+    exercise empty slices, ragged tiles and multi-tile slices, then two consecutive steps (the second reads the row
+    the first one appended through the staged path)."""
+    from faster_qwen3_tts.model import FasterQwen3TTS
+    import torch.nn.functional as F
+    monkeypatch.setenv("FQ3_ATTN_SPLIT", "0")
+    a = FasterQwen3TTS.from_synthetic("0.6B", dtype=torch.bfloat16, with_codec=False, max_seq_len=2048, seed=3).engine
+    monkeypatch.delenv("FQ3_ATTN_SPLIT")
+    b = FasterQwen3TTS.from_synthetic("0.6B", dtype=torch.bfloat16, with_codec=False, max_seq_len=2048, seed=3).engine
+    g = torch.Generator().manual_seed(11)
+    L, nkv = a.talker_cfg["num_hidden_layers"], a.talker_cfg["num_key_value_heads"]
+    H = a.H
+    worst = 0.0
+    for pos in (3, 40, 333, 1100, 2040):
+        for l in range(L):
+            k = torch.randn(nkv, pos, 128, generator=g).to(torch.bfloat16).cuda()
+            v = torch.randn(nkv, pos, 128, generator=g).to(torch.bfloat16).cuda()
+            a.import_kv(l, k, v); b.import_kv(l, k, v)
+        for step in range(2):
+            x = (torch.randn(H, generator=g) * 0.5).to(torch.bfloat16).cuda()
+            ya, yb = a.talker_step(x, pos + step).float(), b.talker_step(x, pos + step).float()
+            assert torch.isfinite(yb).all()
+            err = (ya - yb).abs().max().item()
+            cos = F.cosine_similarity(ya, yb, dim=0).item()
+            print(f"pos {pos + step}: max abs {err:.4f} cos {cos:.6f}")
+            worst = max(worst, err)
+            assert cos > 0.999
+    assert worst < 0.25  # post-norm hidden |x|~3 after 28 bf16 layers; the two paths differ only in rounding order

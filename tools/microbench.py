@@ -53,3 +53,53 @@ def timeline(label, fn, L):
 timeline("talker pos256", lambda: eng.talker_step(x, 256), eng.talker_cfg["num_hidden_layers"])
 timeline("talker pos2000", lambda: eng.talker_step(x, 2000), eng.talker_cfg["num_hidden_layers"])
 timeline("predictor pass1", lambda: eng.predictor_run(pi, SamplingParams(do_sample=False), u), eng.pred_cfg["num_hidden_layers"])
+
+# ---- frame-level phases of one predictor frame (slots 1024 + 8*pass + k)
+for samp in (False, True):
+    eng.debug_enable(2)
+    eng.predictor_run(pi, SamplingParams(do_sample=samp), u)
+    torch.cuda.synchronize()
+    ts = eng.probe_timestamps(1024 + 8 * 16).double()[1024:].view(16, 8)[:15, :5]
+    d = (ts[:, 1:] - ts[:, :-1]) / 1.965e3
+    avg = d[1:].mean(0)
+    print(json.dumps({"what": "pred_pass_us", "do_sample": samp, "embed+mtp": round(float(avg[0]), 2), "layers": round(float(avg[1]), 2),
+                      "head": round(float(avg[2]), 2), "sample": round(float(avg[3]), 2), "pass0_layers": round(float(d[0, 1]), 2)}))
+    eng.debug_enable(0)
+
+# ---- fused on-device loop: chunks of 8 frames at a bench-like context (prompt 232), sampled
+sp = SamplingParams(do_sample=True, top_k=50, temperature=0.9, top_p=1.0, repetition_penalty=1.05)
+spp = SamplingParams(do_sample=True, top_k=50, temperature=0.9, top_p=1.0, repetition_penalty=1.0)
+def fused(n_chunks, chunk=8, prefill=232, dbg=0):
+    eng.begin_request(first_token=5, prefill_len=prefill, gen_step=0, past_hidden=torch.randn(H, device="cuda").bfloat16(),
+                      trailing_text=torch.randn(25, H, device="cuda").bfloat16() * 0.02,
+                      tts_pad=torch.randn(H, device="cuda").bfloat16() * 0.02, max_new_tokens=4096, min_new_tokens=4096,
+                      sp_talker=sp, sp_predictor=spp, uniforms=torch.rand(4097, 16, device="cuda"))
+    eng.debug_enable(dbg)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    n = 0
+    for _ in range(n_chunks):
+        out, res = eng.decode_chunk(chunk)
+        n += out.shape[0]
+    e1.record(); e1.synchronize()
+    eng.debug_enable(0)
+    return e0.elapsed_time(e1) / max(n, 1), n
+fused(2)
+for chunk in (8, 64):
+    msf, n = fused(128 // chunk, chunk)
+    print(json.dumps({"what": "fused_ms_per_frame", "chunk": chunk, "frames": n, "ms": round(msf, 4)}))
+msf, n = fused(1, 8, dbg=2)
+tl = eng.probe_timestamps(12 * 28).double().view(28, 12)[8:]
+dl = ((tl[:, 1:] - tl[:, :-1]) / 1.965e3).mean(0)
+print(json.dumps({"what": "fused_talker_layer_us", **{k: round(float(v), 2) for k, v in zip(
+    ["norm_in", "gemv_qkv", "B1", "attn", "B2", "load+gemv_o", "B3", "norm+gemv_gu", "B4", "load+gemv_dn", "B5"], dl)},
+    "layer_total": round(float(dl.sum()), 2)}))
+ts = eng.probe_timestamps(2048 + 8 * 8).double()[2048:].view(8, 8)[:, :6]
+d = (ts[:, 1:] - ts[:, :-1]) / 1.965e3
+nxt = (ts[1:, 0] - ts[:-1, 5]) / 1.965e3
+avg = d[1:].mean(0)
+print(json.dumps({"what": "fused_frame_us", "predictor": round(float(avg[0]), 1), "embed_sum": round(float(avg[1]), 1),
+                  "talker_layers": round(float(avg[2]), 1), "head": round(float(avg[3]), 1), "sample": round(float(avg[4]), 1),
+                  "loop_top": round(float(nxt.mean()), 1), "frame0_predictor": round(float(d[0, 0]), 1),
+                  "frame0_talker": round(float(d[0, 2]), 1), "chunk_ms_per_frame": round(msf, 4)}))
