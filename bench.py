@@ -331,22 +331,45 @@ def run_b200(args):
     b_stream = t_bytes + kv_bytes + p_bytes
     k_ms = statistics.mean(chunk_ms) if chunk_ms else None
     traffic = None
+    traffic_file = next((f for f in ("r1c_decode_kernel_ncu.csv", "r1b_decode_kernel_ncu.csv")
+                         if os.path.exists(os.path.join(ROOT, "profiles", f))), "r1b_decode_kernel_ncu.csv")
     try:  # DRAM bytes of one launch from the committed ncu capture of this kernel (profiles/)
-        for line in open(os.path.join(ROOT, "profiles", "r1b_decode_kernel_ncu.csv")):
+        for line in open(os.path.join(ROOT, "profiles", traffic_file)):
             f = line.strip().split(",")
             if len(f) == 4 and f[0] == "0" and f[1] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
                 traffic = (traffic or 0.0) + float(f[3]) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[f[2]]
     except Exception:
         traffic = None
+    # the talker step alone (the kernel the north_star's HBM target is stated for): MODE_TALKER_STEP launches at the
+    # run's mean position, bytes = talker layer weights + KV(p) (no head), timed live with CUDA events
+    talker = None
+    try:
+        ppos = int(pbar)
+        xh = torch.randn(tcfg.hidden_size, device=dev).to(torch.bfloat16)
+        for _ in range(3):
+            eng.talker_step(xh, ppos)
+        torch.cuda.synchronize()
+        t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0e.record()
+        for _ in range(20):
+            eng.talker_step(xh, ppos)
+        t1e.record(); t1e.synchronize()
+        ts_ms = t0e.elapsed_time(t1e) / 20
+        ts_bytes = t_bytes - tcfg.vocab_size * tcfg.hidden_size * esz + Lt * 2 * nKV * 128 * esz * (ppos + 1)
+        talker = {"position": ppos, "ms": ts_ms, "bytes": ts_bytes, "achieved": ts_bytes / (ts_ms / 1000) / 1e9,
+                  "frac": ts_bytes / (ts_ms / 1000) / 1e9 / peak,
+                  "note": "one launch per step here (launch + pipeline fill included); inside the fused loop the step is shorter"}
+    except Exception as ex:  # never let the extra measurement break the bench line
+        talker = {"error": str(ex)[:120]}
     roof = None
     if k_ms:
         ach = b_alg * args.chunk / (k_ms / 1000) / 1e9
         roof = {"bound": "hbm", "kernel": "fq3_decode_kernel<bf16> (one launch = one 8-frame chunk)",
                 "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
-                "traffic_source": "ncu --set full capture of one 8-frame launch, profiles/r1b_decode_kernel_ncu.csv",
+                "traffic_source": "ncu --set full capture of one 8-frame launch, profiles/" + traffic_file,
                 "peak_source": peak_kind, "alg_bytes_per_frame": b_alg, "launch_ms": k_ms,
                 "streamed_bytes_per_frame": b_stream, "streamed_frac": b_stream * args.chunk / (k_ms / 1000) / 1e9 / peak,
-                "ms_per_frame": k_ms / args.chunk}
+                "ms_per_frame": k_ms / args.chunk, "talker_step": talker}
     out = {
         "metric": METRIC, "value": value, "unit": "x realtime", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",

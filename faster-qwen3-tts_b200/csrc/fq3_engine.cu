@@ -307,13 +307,14 @@ extern "C" int fq3_engine_create(const fq3_config* cfg, fq3_engine** out) {
   k.max_seq_len = cfg->max_seq_len;
   k.dbg = e->dbg; k.dbg_stride_layer = e->dbg_stride;
   k.pred_pin_layers = 2;
+  if (const char* v = getenv("FQ3_PRED_PIN")) k.pred_pin_layers = std::max(atoi(v), 0);   // tuning knob
   {
     // split-key talker attention (bf16 engines): S CTAs per q-head; a slice must fit the 4 ring tiles it may hold
     int Sx = e->bf16 ? std::min(e->ncta / std::max(T.num_attention_heads, 1), 16) : 0;
     if (Sx < 2 || (cfg->max_seq_len + Sx - 1) / Sx > 4 * KVT_KEYS) Sx = 0;
     if (const char* v = getenv("FQ3_ATTN_SPLIT")) Sx = std::min(Sx, std::max(atoi(v), 0)) < 2 ? 0 : std::min(Sx, atoi(v));
     k.attn_split = Sx;
-    k.attn_split_min = 448;   // measured crossover on B200 (1.7B geometry): per-head CTAs win below ~450 cached keys
+    k.attn_split_min = 192;   // measured on B200 (1.7B geometry): split wins from ~250 cached keys up (0.93 vs 1.01 ms/step at 300)
     if (const char* v = getenv("FQ3_ATTN_SPLIT_MIN")) k.attn_split_min = std::max(atoi(v), 0);
     k.PART = e->PART;
     k.attn_cnt = e->bar + 1024;
