@@ -361,3 +361,34 @@ def test_split_attention_matches_per_head_attention(monkeypatch):
             worst = max(worst, err)
             assert cos > 0.999
     assert worst < 0.25  # post-norm hidden |x|~3 after 28 bf16 layers; the two paths differ only in rounding order
+
+
+@pytest.mark.gpu
+def test_fused_loop_across_split_attention_threshold():
+    """Fused on-device loop, bf16, tiny geometry (4 q-heads -> 16 key slices per head): the context grows from below
+    the split threshold (192 cached keys) through it and across slice/tile boundaries; the producer warp's K/V tile
+    schedule has to stay in lock-step with the consumers for every frame (a mismatch hangs or traps), streaming and
+    non-streaming drivers must agree, and the first frames -- generated before the threshold -- must equal those of
+    an engine with the split path disabled."""
+    cfg = O.cfg_tiny()
+    P, n = 170, 72
+    tie, tth, tpe = O.make_inputs(cfg, P, 6, seed=4, dtype=torch.bfloat16)
+    uniforms = np.random.default_rng(9).random((n + 1, 16), dtype=np.float32)
+    kw = dict(max_new_tokens=n, min_new_tokens=n, do_sample=True)
+    p = Pair(cfg, seed=0, dtype=torch.bfloat16, max_seq_len=512)
+    codes, _ = _run_case(p, tie, tth, tpe, uniforms, **kw)
+    assert codes.shape == (n, 16)
+    assert int(codes[:, 0].max()) < cfg.talker.vocab_size - 1024 and int(codes[:, 1:].max()) < cfg.predictor.vocab_size
+    chunks = [c.cpu() for c, _ in fast_generate_streaming(
+        p.talker, tie[None].cuda(), torch.ones(1, P, dtype=torch.long).cuda(), tth[None].cuda(),
+        tpe[None, None].cuda(), p.config, p.pg, p.tg, chunk_size=8, uniforms=torch.from_numpy(uniforms).cuda(), **kw)]
+    assert torch.equal(torch.cat(chunks), codes)
+    os.environ["FQ3_ATTN_SPLIT"] = "0"
+    try:
+        q = Pair(cfg, seed=0, dtype=torch.bfloat16, max_seq_len=512)
+    finally:
+        del os.environ["FQ3_ATTN_SPLIT"]
+    ref, _ = _run_case(q, tie, tth, tpe, uniforms, **kw)
+    assert torch.equal(ref[: 192 - P], codes[: 192 - P])   # identical code path until 192 keys are cached
+    same = int((ref == codes).all(dim=1).sum())
+    print("frames identical with / without split attention:", same, "of", n)
