@@ -8,14 +8,13 @@ Kept verbatim from the reference: constructor signature, ``from_pretrained`` / `
 Replaced: the two graph objects are thin handles on one fq3 engine (persistent sm_100a kernel); per-chunk work
 is one kernel launch + one codec decode.
 
-Prompt assembly (tokeniser, speaker encoder, ICL prompt; model.py:295-805) is upstream ``qwen-tts`` code that is
-absent from this image; with a synthetic base model (``from_synthetic``) a deterministic stand-in builds prompt
-embeddings of the documented shapes.  With a real upstream model the upstream helpers are called through
-``_prepare_generation_upstream`` (next row, not accelerated here).
+Prompt assembly (model.py:278-805) is restated here and in ``prompt.py`` (embedding layout pinned against the
+reference's own function, tests/test_prompt_cpu.py).  Tokeniser, speaker encoder, codec encoder and the ICL prompt
+are upstream ``qwen-tts`` methods of the wrapped model -- called through exactly the attributes the reference calls;
+the synthetic model (``from_synthetic``) answers them with deterministic stand-ins (``synthetic_frontend.py``).
 """
 from __future__ import annotations
 
-import hashlib
 import logging
 import time
 from pathlib import Path
@@ -162,57 +161,168 @@ class FasterQwen3TTS:
             return 0
         return int(st._lib.fq3_codec_launch_count(st._h))
 
-    # ------------------------------------------------------------------ prompt assembly
+    # ------------------------------------------------------------------ prompt assembly (model.py:278-581)
     def _is_synthetic(self) -> bool:
         return bool(getattr(self.model, "synthetic", False))
 
-    def _synthetic_prompt(self, text: str, ref_text: str, icl: bool, non_streaming_mode: bool, ref_frames: int = 174):
-        """Deterministic stand-in for model.py:583-805: shapes follow SURVEY.md 8(d) (prefix ~9, ICL prompt spans the
-        reference frames, text is fed step by step unless non_streaming_mode)."""
-        cfg = self.model.syn_cfg
-        H = cfg.talker_config.hidden_size
-        n_text = max(1, len(text.split()) * 2)
-        seed = int.from_bytes(hashlib.sha256((text + "|" + ref_text).encode()).digest()[:4], "little")
-        g = torch.Generator().manual_seed(seed)
-        P = 9 + (ref_frames if icl else 1) + (n_text if non_streaming_mode else 0)
-        Tt = 0 if non_streaming_mode else n_text
-        dev = self.engine.device
-        tie = torch.randn(1, P, H, generator=g).to(self.dtype)
-        tth = torch.randn(1, max(Tt, 1), H, generator=g).to(self.dtype)[:, :Tt]
-        tpe = torch.randn(1, 1, H, generator=g).to(self.dtype)
-        ref_codes = torch.randint(0, cfg.code_predictor_config.vocab_size, (ref_frames, 16), generator=g) if icl else None
-        return (tie.to(dev), torch.ones(1, P, dtype=torch.long, device=dev), tth.to(dev), tpe.to(dev),
-                None if ref_codes is None else ref_codes.to(dev))
+    @staticmethod
+    def _read_audio(path) -> Tuple[np.ndarray, int]:
+        """float32 samples + rate.  soundfile when installed (the reference's reader), else 16-bit PCM WAV via stdlib."""
+        try:
+            import soundfile as sf
+            return sf.read(str(path), dtype="float32", always_2d=False)
+        except ImportError:
+            import wave
+            with wave.open(str(path), "rb") as w:
+                if w.getsampwidth() != 2:
+                    raise ValueError("without soundfile only 16-bit PCM WAV reference audio can be read")
+                raw = np.frombuffer(w.readframes(w.getnframes()), dtype="<i2").astype(np.float32) / 32768.0
+                if w.getnchannels() > 1:
+                    raw = raw.reshape(-1, w.getnchannels())
+                return raw, w.getframerate()
+
+    def _load_ref_audio_with_silence(self, ref_audio, silence_secs: float = 0.5) -> Tuple[np.ndarray, int]:
+        """model.py:278-293: mono, optionally followed by silence so the ICL prompt does not end mid-phoneme."""
+        audio, sr = self._read_audio(ref_audio)
+        if audio.ndim > 1:
+            audio = audio.mean(axis=1)
+        if silence_secs > 0:
+            audio = np.concatenate([audio, np.zeros(int(silence_secs * sr), dtype=np.float32)])
+        return audio, sr
+
+    def _resolve_voice_clone_prompt(self, input_ids, ref_audio, ref_text: str, xvec_only: bool, append_silence: bool,
+                                    voice_clone_prompt):
+        """-> (prompt dict, ref_ids, using_icl_mode)   (model.py:295-320)"""
+        if voice_clone_prompt is not None:
+            return self._resolve_precomputed_voice_clone_prompt(input_ids=input_ids, ref_text=ref_text,
+                                                                voice_clone_prompt=voice_clone_prompt)
+        if ref_audio is None:
+            raise ValueError("ref_audio is required when voice_clone_prompt is not provided")
+        return self._resolve_voice_clone_prompt_from_reference(input_ids=input_ids, ref_audio=ref_audio,
+                                                               ref_text=ref_text, xvec_only=xvec_only,
+                                                               append_silence=append_silence)
+
+    def _ref_ids_for(self, ref_text: str):
+        return self.model._tokenize_texts([self.model._build_ref_text(ref_text)])[0]
+
+    def _resolve_precomputed_voice_clone_prompt(self, input_ids, ref_text: str, voice_clone_prompt):
+        """model.py:322-413: a list of prompt items or a dict of per-request lists; validates the mode flags."""
+        n = len(input_ids)
+        if isinstance(voice_clone_prompt, list):
+            if len(voice_clone_prompt) != n:
+                raise ValueError(f"voice_clone_prompt must have length {n}, got {len(voice_clone_prompt)}")
+            vcp = self.model._prompt_items_to_voice_clone_prompt(voice_clone_prompt)
+            ref_ids = []
+            for item in voice_clone_prompt:
+                if not bool(item.icl_mode):
+                    ref_ids.append(None)
+                    continue
+                item_text = item.ref_text if item.ref_text else ref_text
+                if not item_text:
+                    raise ValueError("ref_text is required when voice_clone_prompt uses ICL mode.")
+                ref_ids.append(self._ref_ids_for(item_text))
+            return vcp, ref_ids, any(vcp["icl_mode"])
+
+        required = ("ref_spk_embedding",)
+        missing = [k for k in required if k not in voice_clone_prompt]
+        if missing:
+            raise ValueError(f"voice_clone_prompt missing required keys: {missing}. Expected keys: {list(required)}")
+        for key in ("ref_spk_embedding", "x_vector_only_mode", "icl_mode", "ref_code"):
+            if key in voice_clone_prompt:
+                value = voice_clone_prompt[key]
+                if not isinstance(value, list) or len(value) != n:
+                    raise ValueError(f"voice_clone_prompt[{key!r}] must be a list with length {n}")
+        xvec = voice_clone_prompt.get("x_vector_only_mode", [True] * n)
+        if "icl_mode" in voice_clone_prompt:
+            icl = [bool(v) for v in voice_clone_prompt["icl_mode"]]
+            for i, (x, c) in enumerate(zip(xvec, icl)):
+                if bool(x) == bool(c):
+                    raise ValueError(f"voice_clone_prompt has inconsistent mode flags at index {i}: "
+                                     "x_vector_only_mode and icl_mode must be opposites")
+        else:
+            icl = [not bool(v) for v in xvec]
+        codes = voice_clone_prompt.get("ref_code", [None] * n)
+        for i, (x, c, code) in enumerate(zip(xvec, icl, codes)):
+            if bool(x) and code is not None:
+                raise ValueError(f"voice_clone_prompt index {i}: ref_code must be None in x_vector_only mode")
+            if bool(c) and code is None:
+                raise ValueError(f"voice_clone_prompt index {i}: ref_code is required in ICL mode")
+        vcp = dict(ref_code=codes, ref_spk_embedding=voice_clone_prompt["ref_spk_embedding"],
+                   x_vector_only_mode=[bool(v) for v in xvec], icl_mode=[bool(v) for v in icl])
+        if not any(vcp["icl_mode"]):
+            return vcp, [None] * n, False
+        if not ref_text:
+            raise ValueError("ref_text is required when voice_clone_prompt uses ICL mode.")
+        shared = self._ref_ids_for(ref_text)        # one ref_text is shared by every ICL item of the batch
+        return vcp, [shared if c else None for c in vcp["icl_mode"]], True
+
+    def _resolve_voice_clone_prompt_from_reference(self, input_ids, ref_audio, ref_text: str, xvec_only: bool,
+                                                   append_silence: bool):
+        """model.py:415-463: speaker vector (+ codec frames and reference-text ids for ICL), cached per reference."""
+        using_icl = not xvec_only
+        key = (str(ref_audio), ref_text, xvec_only, append_silence)
+        if key in self._voice_prompt_cache:
+            vcp, ref_ids = self._voice_prompt_cache[key]
+            return vcp, ref_ids, using_icl
+        if xvec_only:
+            items = self.model.create_voice_clone_prompt(ref_audio=str(ref_audio), ref_text="", x_vector_only_mode=True)
+            vcp = dict(ref_code=[None], ref_spk_embedding=[items[0].ref_spk_embedding], x_vector_only_mode=[True],
+                       icl_mode=[False])
+            ref_ids = [None] * len(input_ids)
+        else:
+            try:
+                audio_in = self._load_ref_audio_with_silence(ref_audio, silence_secs=0.5 if append_silence else 0.0)
+            except (OSError, EOFError, ValueError):
+                if not self._is_synthetic():
+                    raise
+                audio_in = str(ref_audio)   # synthetic voices are derived from the name; nothing has to be readable
+            items = self.model.create_voice_clone_prompt(ref_audio=audio_in, ref_text=ref_text)
+            vcp = self.model._prompt_items_to_voice_clone_prompt(items)
+            rt = items[0].ref_text
+            ref_ids = [self._ref_ids_for(rt) if rt else None]
+        self._voice_prompt_cache[key] = (vcp, ref_ids)
+        return vcp, ref_ids, using_icl
 
     def _prepare_generation(self, text, ref_audio=None, ref_text="", language="English", xvec_only=False,
                             non_streaming_mode=False, append_silence=True, voice_clone_prompt=None, instruct=None):
+        """Inputs of the decode path for voice cloning (model.py:465-543); `xvec_only` is ignored when a precomputed
+        `voice_clone_prompt` is given."""
+        from .prompt import build_talker_inputs
+        input_ids = self.model._tokenize_texts([self.model._build_assistant_text(text)])
+        instruct_ids = [None]
+        if instruct:
+            instruct_ids = [self.model._tokenize_texts([self.model._build_instruct_text(instruct)])[0]]
+        vcp, ref_ids, using_icl = self._resolve_voice_clone_prompt(
+            input_ids=input_ids, ref_audio=ref_audio, ref_text=ref_text, xvec_only=xvec_only,
+            append_silence=append_silence, voice_clone_prompt=voice_clone_prompt)
+        if instruct and not using_icl:
+            logger.warning("Base-model instruct with x-vector-only voice cloning is experimental; prefer xvec_only=False "
+                           "(ICL mode) when using instruct for voice cloning.")
         m = self.model.model
-        if self._is_synthetic():
-            icl = not xvec_only and (ref_audio is not None or (voice_clone_prompt or {}).get("ref_code") is not None)
-            if voice_clone_prompt is None and ref_audio is None:
-                raise ValueError("ref_audio is required when voice_clone_prompt is not provided")
-            tie, tam, tth, tpe, ref_codes = self._synthetic_prompt(text, ref_text, icl, non_streaming_mode)
-        else:
-            tie, tam, tth, tpe, ref_codes = self._prepare_generation_upstream(
-                text, ref_audio, ref_text, language, xvec_only, non_streaming_mode, append_silence, voice_clone_prompt,
-                instruct)
+        tie, tam, tth, tpe = build_talker_inputs(
+            m, input_ids=input_ids, ref_ids=ref_ids, voice_clone_prompt=vcp,
+            languages=[language] if language is not None else ["Auto"], speakers=None,
+            non_streaming_mode=non_streaming_mode, instruct_ids=instruct_ids)
         if not self._warmed_up:
             self.warmup(tie.shape[1])
         talker = m.talker
         talker.rope_deltas = None
+        ref_codes = None   # ICL: the decoder gets the reference frames as acoustic context (model.py:536-539)
+        if using_icl and vcp.get("ref_code") and vcp["ref_code"][0] is not None:
+            ref_codes = vcp["ref_code"][0]
         return m, talker, m.config.talker_config, tie, tam, tth, tpe, ref_codes
 
-    def _prepare_generation_upstream(self, *a, **k):
-        raise NotImplementedError(
-            "prompt assembly against upstream qwen-tts (model.py:295-805 of the reference) is not part of the "
-            "accelerated hot path and cannot be exercised offline; see SURVEY.md section 8(f) item 1")
-
     def _prepare_generation_custom(self, text, language, speaker, instruct=None, non_streaming_mode=True):
+        """Inputs for custom-voice / voice-design requests (model.py:545-581)."""
+        from .prompt import build_talker_inputs
+        input_ids = self.model._tokenize_texts([self.model._build_assistant_text(text)])
+        instruct_ids = [None if instruct is None or instruct == "" else
+                        self.model._tokenize_texts([self.model._build_instruct_text(instruct)])[0]]
         m = self.model.model
-        if not self._is_synthetic():
-            self._prepare_generation_upstream()
-        tie, tam, tth, tpe, _ = self._synthetic_prompt(text + "|" + str(speaker) + "|" + str(instruct), "", False,
-                                                       non_streaming_mode)
+        tie, tam, tth, tpe = build_talker_inputs(
+            m, input_ids=input_ids, ref_ids=[None], voice_clone_prompt=None,
+            languages=[language] if language is not None else ["Auto"], speakers=[speaker],
+            non_streaming_mode=non_streaming_mode, instruct_ids=instruct_ids)
         if not self._warmed_up:
             self.warmup(tie.shape[1])
         m.talker.rope_deltas = None

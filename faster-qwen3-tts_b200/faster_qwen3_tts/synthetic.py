@@ -9,6 +9,9 @@ attribute paths the reference (and ``weights.py``) touch on the real model:
     base.model.talker.code_predictor.{model, lm_head[15], small_to_mtp_projection, get_input_embeddings()}
     base.model.talker.forward(inputs_embeds=..., attention_mask=..., ...)   (prefill, generate.py:107-118)
     base.model.config.talker_config          base.model.speech_tokenizer.decode({"audio_codes": ...})
+    base.model.talker.{get_text_embeddings(), text_projection}, base.model.{generate_speaker_prompt,
+    generate_icl_prompt}, base.{_tokenize_texts, _build_assistant_text, _build_ref_text, _build_instruct_text,
+    create_voice_clone_prompt, _prompt_items_to_voice_clone_prompt}          (prompt assembly, model.py:295-805)
 
 ``SynTalker.forward`` is the variable-length prefill; like the reference's prefill (upstream HF eager forward) it
 is plain library ops (torch / cuBLAS) -- the engine takes over from the first decode step.
@@ -46,9 +49,22 @@ def make_config(size: str = "1.7B", *, talker_vocab: int = 3072, pred_vocab: int
     t = stack(th, ti, tl, talker_vocab)
     t.codec_eos_token_id = eos
     t.num_code_groups = 16
+    # special ids of the codec vocabulary used by prompt assembly (model.py:628-690); the real values come from the
+    # checkpoint's config.json, these only have to be distinct, inside the special range and different from eos
+    base = talker_vocab - 1024 if talker_vocab > 1024 else talker_vocab - 32
+    t.codec_pad_id, t.codec_bos_id = eos - 2, eos - 1
+    t.codec_think_id, t.codec_nothink_id, t.codec_think_bos_id, t.codec_think_eos_id = eos + 4, eos + 5, eos + 6, eos + 7
+    t.codec_language_id = {"chinese": base + 2, "english": base + 3, "german": base + 4, "japanese": base + 5,
+                           "cantonese": base + 6}
+    t.spk_id = {"vivian": base + 20, "ryan": base + 21, "uncle_fu": base + 22, "aiden": base + 23, "serena": base + 24}
+    t.spk_is_dialect = {"vivian": False, "ryan": False, "uncle_fu": "cantonese", "aiden": False, "serena": False}
+    t.text_vocab_size = 512 if size == "tiny" else 4096
+    t.text_hidden_size = 256 if size == "tiny" else 2048
     p = stack(ph, pi, pl, pred_vocab)
     p.num_code_groups = 16
-    return types.SimpleNamespace(talker_config=t, code_predictor_config=p, has_mtp=mtp)
+    # text-side special ids (model.py:641-649)
+    return types.SimpleNamespace(talker_config=t, code_predictor_config=p, has_mtp=mtp,
+                                 tts_bos_token_id=8, tts_eos_token_id=9, tts_pad_token_id=10)
 
 
 class RMSNorm(nn.Module):
@@ -158,12 +174,26 @@ class CodePredictor(nn.Module):
         return self.model.codec_embedding
 
 
+class TextProjection(nn.Module):
+    """text hidden -> talker hidden, two biased linears with SiLU in between (stand-in for upstream's resize MLP)"""
+
+    def __init__(self, d_in, d_out):
+        super().__init__()
+        self.linear_fc1 = _lin(d_in, d_out, bias=True)
+        self.linear_fc2 = _lin(d_out, d_out, bias=True)
+
+    def forward(self, x):
+        return self.linear_fc2(F.silu(self.linear_fc1(x)))
+
+
 class Talker(nn.Module):
     def __init__(self, cfg):
         super().__init__()
         tc = cfg.talker_config
         self.config = tc
         self.model = Stack(tc, embed_tables=1, embed_dim=tc.hidden_size)
+        self.text_embedding = nn.Embedding(getattr(tc, "text_vocab_size", 512), getattr(tc, "text_hidden_size", 256))
+        self.text_projection = TextProjection(self.text_embedding.embedding_dim, tc.hidden_size)
         self.codec_head = _lin(tc.hidden_size, tc.vocab_size)
         self.code_predictor = CodePredictor(cfg.code_predictor_config, tc.hidden_size, cfg.has_mtp,
                                             tc.num_code_groups - 1)
@@ -171,6 +201,13 @@ class Talker(nn.Module):
 
     def get_input_embeddings(self):
         return self.model.codec_embedding
+
+    def get_text_embeddings(self):
+        return self.text_embedding
+
+    @property
+    def device(self):
+        return self.codec_head.weight.device
 
     @torch.no_grad()
     def forward(self, inputs_embeds=None, attention_mask=None, trailing_text_hidden=None, tts_pad_embed=None,
@@ -201,7 +238,12 @@ def build_base_model(cfg, state: Optional[Dict[str, torch.Tensor]] = None, *, se
         sd = {k[len("talker."):]: v for k, v in state.items() if k.startswith("talker.")}
         missing, unexpected = talker.load_state_dict(sd, strict=False)
         assert not unexpected, unexpected
-        assert not missing, missing
+        front = [k for k in missing if k.startswith(("text_embedding", "text_projection"))]
+        assert len(front) == len(missing), [k for k in missing if k not in front]
+        g = torch.Generator(device=dev).manual_seed(seed + 77)   # the oracle's weight sets have no text front end
+        for name, p in talker.named_parameters():
+            if name in front:
+                p.normal_(0.0, 0.5 if "embedding" in name else std, generator=g)
     else:
         g = torch.Generator(device=dev).manual_seed(seed)
         for name, p in talker.named_parameters():
@@ -209,14 +251,20 @@ def build_base_model(cfg, state: Optional[Dict[str, torch.Tensor]] = None, *, se
                 p.fill_(1.0)
             elif "codec_embedding" in name:
                 p.normal_(0.0, 1.0, generator=g)
+            elif "text_embedding" in name:
+                p.normal_(0.0, 0.5, generator=g)
             elif "codec_head" in name or "lm_head" in name:
                 p.normal_(0.0, std * 4, generator=g)
             else:
                 p.normal_(0.0, std, generator=g)
     talker = talker.to(dtype=dtype)
-    inner = types.SimpleNamespace(talker=talker, config=types.SimpleNamespace(talker_config=cfg.talker_config),
-                                  speech_tokenizer=speech_tokenizer)
-    return types.SimpleNamespace(model=inner, synthetic=True)
+    from .synthetic_frontend import SyntheticInner, SyntheticOuter
+    icfg = types.SimpleNamespace(talker_config=cfg.talker_config,
+                                 tts_bos_token_id=getattr(cfg, "tts_bos_token_id", 8),
+                                 tts_eos_token_id=getattr(cfg, "tts_eos_token_id", 9),
+                                 tts_pad_token_id=getattr(cfg, "tts_pad_token_id", 10))
+    inner = SyntheticInner(talker=talker, config=icfg, speech_tokenizer=speech_tokenizer)
+    return SyntheticOuter(inner)
 
 
 def make_prompt(cfg, P: int, Tt: int, seed: int = 0, dtype=torch.bfloat16, device="cpu"):

@@ -16,7 +16,12 @@ indexing, max_seq_len stop, chunking).  torch.multinomial inside the reference's
 by the inverse-CDF noise contract (its Philox stream is not reproducible); the probabilities it was handed are
 recorded, which pins suppress/temperature/top-k/top-p/softmax bit for bit.
 
-Usage:  python oracle/make_golden.py            (writes tests/golden/sampling.npz, tests/golden/loop.npz)
+  * faster_qwen3_tts/model.py      FasterQwen3TTS._build_talker_inputs_local (prompt assembly, model.py:583-805),
+                                   driven on the synthetic module tree (oracle/prompt_cases.py); `soundfile`, which
+                                   model.py imports at module level and the image lacks, is stubbed (it is not used
+                                   by that function)
+
+Usage:  python oracle/make_golden.py            (writes tests/golden/{sampling,loop,prompt}.npz)
 """
 from __future__ import annotations
 
@@ -244,6 +249,39 @@ def gen_loop(ref, out_path):
     smp.torch = torch
 
 
+# ----------------------------------------------------------------------------------------------
+# prompt assembly fixtures
+# ----------------------------------------------------------------------------------------------
+
+
+def load_reference_model_class():
+    """The reference's FasterQwen3TTS class, loaded by file path with `soundfile` stubbed."""
+    if "soundfile" not in sys.modules:
+        sys.modules["soundfile"] = types.ModuleType("soundfile")
+    for name in ("utils", "model"):
+        spec = importlib.util.spec_from_file_location(f"fq3ref.{name}", f"{REF}/{name}.py")
+        m = importlib.util.module_from_spec(spec)
+        sys.modules[f"fq3ref.{name}"] = m
+        spec.loader.exec_module(m)
+    return sys.modules["fq3ref.model"].FasterQwen3TTS
+
+
+def gen_prompt(out_path):
+    from oracle import prompt_cases as PC
+    ref_cls = load_reference_model_class()
+    base = PC.build_base(seed=0)
+    out = {}
+    names = []
+    for name, kw in PC.cases(base).items():
+        tie, tam, tth, tpe = ref_cls._build_talker_inputs_local(None, base.model, **kw)
+        out[name + "_tie"], out[name + "_tam"] = tie.numpy(), tam.numpy()
+        out[name + "_tth"], out[name + "_tpe"] = tth.numpy(), tpe.numpy()
+        names.append(name)
+        print(f"{name}: embeds {tuple(tie.shape)} mask_sum {tam.sum(1).tolist()} trailing {tuple(tth.shape)}")
+    out["names"] = np.array(names)
+    np.savez_compressed(out_path, **out)
+
+
 if __name__ == "__main__":
     ref = load_reference()
     gdir = os.path.join(ROOT, "tests", "golden")
@@ -251,3 +289,4 @@ if __name__ == "__main__":
     with torch.inference_mode():
         gen_sampling(ref, os.path.join(gdir, "sampling.npz"))
         gen_loop(ref, os.path.join(gdir, "loop.npz"))
+        gen_prompt(os.path.join(gdir, "prompt.npz"))
