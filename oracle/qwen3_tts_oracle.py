@@ -22,8 +22,14 @@ rotate_half/apply :816-820,1448-1470).
 PARITY STATUS
   * sampling + loop control flow: PINNED against the reference's own ``sampling.py`` / ``generate.py`` /
     ``streaming.py`` executed in this container (``oracle/make_golden.py`` -> ``tests/golden/*.npz``).
-  * layer arithmetic (talker / predictor / codec): "parity unpinned" -- no weights, no ``qwen_tts`` and no
-    golden token/PCM vectors exist in the reference tree.
+  * prompt assembly: the product's restatement is PINNED against the reference's own
+    ``_build_talker_inputs_local`` executed here (``tests/golden/prompt.npz``, ``tests/test_prompt_cpu.py``).
+  * talker / predictor layer arithmetic (``run_stack``): checked at test time against the Hugging Face eager Qwen3
+    decoder of the in-image ``transformers`` (same weights; prefill + cached steps): bit-identical in fp32, bf16-ulp
+    level in bf16 (``tests/test_oracle_vs_transformers.py``).  That pins the block to an independent implementation
+    of the architecture family; against upstream ``qwen-tts`` itself it stays "parity unpinned" -- no weights, no
+    ``qwen_tts`` and no golden token/PCM vectors exist in the reference tree.
+  * codec decoder: "parity unpinned" (restated from the Qwen3-Omni Code2Wav analogue).
 
 Noise contract (replaces ``torch.multinomial`` whose CUDA Philox stream cannot be reproduced):
   one uniform u in [0,1) per draw; token = first index v (ascending) whose inclusive prefix sum of the
