@@ -29,7 +29,8 @@ PARITY STATUS
     level in bf16 (``tests/test_oracle_vs_transformers.py``).  That pins the block to an independent implementation
     of the architecture family; against upstream ``qwen-tts`` itself it stays "parity unpinned" -- no weights, no
     ``qwen_tts`` and no golden token/PCM vectors exist in the reference tree.
-  * codec decoder: "parity unpinned" (restated from the Qwen3-Omni Code2Wav analogue).
+  * codec decoder (product-side torch module ``codec.py``): checked against the Hugging Face Qwen3-Omni Code2Wav
+    analogue with shared weights (``tests/test_codec_vs_transformers.py``); "parity unpinned" against upstream.
 
 Noise contract (replaces ``torch.multinomial`` whose CUDA Philox stream cannot be reproduced):
   one uniform u in [0,1) per draw; token = first index v (ascending) whose inclusive prefix sum of the
