@@ -26,7 +26,8 @@ PARITY STATUS
     ``_build_talker_inputs_local`` executed here (``tests/golden/prompt.npz``, ``tests/test_prompt_cpu.py``).
   * talker / predictor layer arithmetic (``run_stack``): checked at test time against the Hugging Face eager Qwen3
     decoder of the in-image ``transformers`` (same weights; prefill + cached steps): bit-identical in fp32, bf16-ulp
-    level in bf16 (``tests/test_oracle_vs_transformers.py``).  That pins the block to an independent implementation
+    level in bf16; ``predictor_frame`` against the Hugging Face Qwen3-Omni talker code predictor stepped with the
+    same weights: identical greedy codes (``tests/test_oracle_vs_transformers.py``).  That pins the block to an independent implementation
     of the architecture family; against upstream ``qwen-tts`` itself it stays "parity unpinned" -- no weights, no
     ``qwen_tts`` and no golden token/PCM vectors exist in the reference tree.
   * codec decoder (product-side torch module ``codec.py``): checked against the Hugging Face Qwen3-Omni Code2Wav

@@ -78,3 +78,45 @@ def test_kv_cache_rows_match_hf_cache():
         ok = cache.k[li].reshape(hk.shape[1], -1, sc.head_dim) if cache.k[li].dim() != 3 else cache.k[li]
         ov = cache.v[li].reshape(hv.shape[1], -1, sc.head_dim) if cache.v[li].dim() != 3 else cache.v[li]
         assert (ok - hk[0]).abs().max() < 1e-5 and (ov - hv[0]).abs().max() < 1e-5
+
+
+def test_predictor_15_step_loop_matches_hf_code_predictor():
+    """The code predictor's per-frame loop (predictor_graph.py:115-167: 2-token prefill [past_hidden, embed(cb0)], then
+    14 single-token steps where step i embeds the previous code with table i-1 and reads head i) against the Hugging Face
+    Qwen3-Omni talker code predictor driven step by step with the same weights, greedy, fp32: identical codes and
+    logits.  (That analogue has no small_to_mtp_projection, so the geometry used here has equal talker / predictor
+    widths -- the 0.6B case, where the projection is the identity.)"""
+    import dataclasses
+    from transformers.models.qwen3_omni_moe import configuration_qwen3_omni_moe as Cf, modeling_qwen3_omni_moe as M
+    base = O.cfg_tiny()
+    cfg = dataclasses.replace(base, talker=dataclasses.replace(base.talker, hidden_size=base.predictor.hidden_size),
+                              has_mtp_projection=False)
+    pc = cfg.predictor
+    W = O.make_weights(cfg, seed=6, dtype=torch.float32)
+    hcfg = Cf.Qwen3OmniMoeTalkerCodePredictorConfig(
+        vocab_size=pc.vocab_size, hidden_size=pc.hidden_size, intermediate_size=pc.intermediate_size,
+        num_hidden_layers=pc.num_hidden_layers, num_attention_heads=pc.num_attention_heads,
+        num_key_value_heads=pc.num_key_value_heads, head_dim=pc.head_dim, rms_norm_eps=pc.rms_norm_eps,
+        rope_parameters={"rope_theta": pc.rope_theta, "rope_type": "default"}, max_position_embeddings=64,
+        num_code_groups=cfg.num_code_groups)
+    hcfg._attn_implementation = "eager"
+    hf = M.Qwen3OmniMoeTalkerCodePredictorModelForConditionalGeneration(hcfg).eval()
+    pre = "talker.code_predictor."
+    missing, unexpected = hf.load_state_dict({k[len(pre):]: v for k, v in W.items() if k.startswith(pre)}, strict=False)
+    assert not missing and not unexpected, (missing, unexpected)
+    om = O.OracleModel(cfg, W)
+    g = torch.Generator().manual_seed(2)
+    for trial in range(3):
+        past_hidden = torch.randn(pc.hidden_size, generator=g)
+        cb0 = int(torch.randint(0, pc.vocab_size, (1,), generator=g))
+        last_id_hidden = om.codec_embed(cb0)
+        dbg = {}
+        with torch.inference_mode():
+            mine = om.predictor_frame(past_hidden, last_id_hidden, O.SamplingParams(do_sample=False))
+            out = hf(inputs_embeds=torch.stack([past_hidden, last_id_hidden])[None], use_cache=True)
+            theirs = [int(out.logits[0, -1].argmax())]
+            for i in range(1, cfg.num_code_groups - 1):
+                out = hf(input_ids=torch.tensor([[theirs[-1]]]), past_key_values=out.past_key_values, use_cache=True,
+                         generation_steps=i)
+                theirs.append(int(out.logits[0, -1].argmax()))
+        assert mine == theirs, (trial, mine, theirs)
