@@ -120,3 +120,23 @@ def test_predictor_15_step_loop_matches_hf_code_predictor():
                          generation_steps=i)
                 theirs.append(int(out.logits[0, -1].argmax()))
         assert mine == theirs, (trial, mine, theirs)
+
+
+def test_three_identical_mrope_streams_equal_plain_rope_tables():
+    """talker_graph.py:53,210-211 feeds the same position on the three mRoPE axes; with the interleaved-mRoPE module
+    of the Hugging Face talker that must equal the plain RoPE tables the oracle (`rope_tables`) and the engine's
+    host side (`weights.rope_tables`) build -- including a rope_delta offset (negative positions are clamped by the
+    callers, not here)."""
+    from transformers.models.qwen3_omni_moe import configuration_qwen3_omni_moe as Cf, modeling_qwen3_omni_moe as M
+    from oracle import prompt_cases  # noqa: F401  (puts the product package on sys.path)
+    from faster_qwen3_tts.weights import rope_tables as product_tables
+    tcfg = Cf.Qwen3OmniMoeTalkerTextConfig(hidden_size=512, num_attention_heads=4, num_key_value_heads=2, head_dim=128,
+                                           rope_parameters={"rope_theta": 1_000_000.0, "rope_type": "default",
+                                                            "mrope_section": [24, 20, 20]})
+    rot = M.Qwen3OmniMoeTalkerRotaryEmbedding(tcfg)
+    pos = torch.tensor([[0, 1, 2, 17, 255, 1000, 2047]]) + 3          # "+3": a rope_delta
+    cos, sin = rot(torch.zeros(1, 1, 128), pos[None].expand(3, -1, -1))
+    oc, os_ = O.rope_tables(128, 1_000_000.0, 4096)
+    assert torch.equal(cos[0], oc[pos[0]]) and torch.equal(sin[0], os_[pos[0]])
+    pc, ps = product_tables(1_000_000.0, 4096, 128)
+    assert torch.equal(torch.as_tensor(pc)[pos[0]].float(), oc[pos[0]]) and torch.equal(torch.as_tensor(ps)[pos[0]].float(), os_[pos[0]])
