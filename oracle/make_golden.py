@@ -21,7 +21,11 @@ recorded, which pins suppress/temperature/top-k/top-p/softmax bit for bit.
                                    model.py imports at module level and the image lacks, is stubbed (it is not used
                                    by that function)
 
-Usage:  python oracle/make_golden.py            (writes tests/golden/{sampling,loop,prompt}.npz)
+  * faster_qwen3_tts/model.py      the body of generate_voice_clone_streaming (hybrid Phase-1 / Phase-2 codec window
+                                   policy, model.py:1052-1135) with request preparation, token stream and codec
+                                   decoder replaced by deterministic doubles (oracle/window_cases.py)
+
+Usage:  python oracle/make_golden.py            (writes tests/golden/{sampling,loop,prompt,window}.npz)
 """
 from __future__ import annotations
 
@@ -282,6 +286,48 @@ def gen_prompt(out_path):
     np.savez_compressed(out_path, **out)
 
 
+# ----------------------------------------------------------------------------------------------
+# streaming codec-window policy fixtures
+# ----------------------------------------------------------------------------------------------
+
+
+def gen_window(out_path):
+    """Runs the body of the reference's generate_voice_clone_streaming (model.py:1019-1137) with a fake `self`:
+    request preparation and the token generator are doubles, the Phase-1 / Phase-2 window logic is the reference's."""
+    from oracle import window_cases as WC
+    ref_cls = load_reference_model_class()
+    streaming_mod = sys.modules["fq3ref.streaming"]
+    real_stream = streaming_mod.fast_generate_streaming
+    out, names = {}, []
+    try:
+        for name, (chunk_size, sizes, n_ref, tk) in WC.CASES.items():
+            tok = WC.FakeTokenizer(**tk)
+            ref_codes = WC.ref_codes_for(n_ref)
+            chunks = WC.chunk_stream(sizes, seed=len(name))
+            streaming_mod.fast_generate_streaming = lambda **kw: iter(chunks)
+            fake = types.SimpleNamespace(
+                _reject_ggml_cached_reference_args=lambda **kw: None,
+                _resolve_non_streaming_mode=lambda v, default: default,
+                _prepare_generation=lambda **kw: (types.SimpleNamespace(speech_tokenizer=tok), None, None, None, None,
+                                                  None, None, ref_codes),
+                predictor_graph=None, talker_graph=None)
+            got = list(ref_cls.generate_voice_clone_streaming.__wrapped__(fake, "text", "English", ref_audio="x.wav",
+                                                                          chunk_size=chunk_size)
+                       if hasattr(ref_cls.generate_voice_clone_streaming, "__wrapped__") else
+                       ref_cls.generate_voice_clone_streaming(fake, "text", "English", ref_audio="x.wav",
+                                                              chunk_size=chunk_size))
+            lens = [len(a) for a, _, _ in got]
+            out[name + "_lens"] = np.array(lens, dtype=np.int64)
+            out[name + "_audio"] = np.concatenate([np.asarray(a, dtype=np.float32) for a, _, _ in got])
+            out[name + "_decoded_T"] = np.array(tok.calls, dtype=np.int64)
+            names.append(name)
+            print(f"{name}: chunk lens {lens} decode calls (frames) {tok.calls}")
+    finally:
+        streaming_mod.fast_generate_streaming = real_stream
+    out["names"] = np.array(names)
+    np.savez_compressed(out_path, **out)
+
+
 if __name__ == "__main__":
     ref = load_reference()
     gdir = os.path.join(ROOT, "tests", "golden")
@@ -290,3 +336,4 @@ if __name__ == "__main__":
         gen_sampling(ref, os.path.join(gdir, "sampling.npz"))
         gen_loop(ref, os.path.join(gdir, "loop.npz"))
         gen_prompt(os.path.join(gdir, "prompt.npz"))
+        gen_window(os.path.join(gdir, "window.npz"))
