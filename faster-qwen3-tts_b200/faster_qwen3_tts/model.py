@@ -470,6 +470,22 @@ class FasterQwen3TTS:
         if t is None and not self._is_synthetic():
             raise ValueError(msg)
 
+    def _validate(self, language, speaker=None, check_speaker=False):
+        """upstream's own validators, called exactly where the reference calls them (model.py:1158-1159,1243-1244,
+        1346,1426); a wrapped model without them (duck-typed test doubles) is not validated."""
+        v = getattr(self.model, "_validate_languages", None)
+        if v is not None:
+            v([language])
+        if check_speaker:
+            v = getattr(self.model, "_validate_speakers", None)
+            if v is not None:
+                v([speaker])
+
+    def _drop_instruct_for_small_model(self, instruct):
+        """model.py:1166-1167,1251-1252: the 0.6B custom-voice checkpoint ignores instructions"""
+        size = getattr(self.model.model, "tts_model_size", None)
+        return None if size is not None and size in "0b6" else instruct
+
     def _simple(self, prep_text, speaker, instruct, language, nsm_default, non_streaming_mode, gen):
         nsm = self._resolve_non_streaming_mode(non_streaming_mode, default=nsm_default)
         m, talker, config, tie, tam, tth, tpe = self._prepare_generation_custom(
@@ -482,6 +498,8 @@ class FasterQwen3TTS:
                               min_new_tokens: int = 2, temperature: float = 0.9, top_k: int = 50, top_p: float = 1.0,
                               do_sample: bool = True, repetition_penalty: float = 1.05) -> Tuple[list, int]:
         self._require_type("custom_voice", "Loaded model does not support custom voice generation")
+        self._validate(language, speaker, check_speaker=True)
+        instruct = self._drop_instruct_for_small_model(instruct)
         from .generate import fast_generate
         m, talker, config, tie, tam, tth, tpe = self._simple(text, speaker, instruct, language, True,
                                                               non_streaming_mode, None)
@@ -502,6 +520,8 @@ class FasterQwen3TTS:
                                         top_p: float = 1.0, do_sample: bool = True, repetition_penalty: float = 1.05,
                                         chunk_size: int = 12) -> Generator[Tuple[np.ndarray, int, dict], None, None]:
         self._require_type("custom_voice", "Loaded model does not support custom voice generation")
+        self._validate(language, speaker, check_speaker=True)
+        instruct = self._drop_instruct_for_small_model(instruct)
         m, talker, config, tie, tam, tth, tpe = self._simple(text, speaker, instruct, language, True,
                                                               non_streaming_mode, None)
         yield from self.stream_from_embeds(tie, tam, tth, tpe, ref_codes=None, chunk_size=chunk_size,
@@ -515,6 +535,7 @@ class FasterQwen3TTS:
                               min_new_tokens: int = 2, temperature: float = 0.9, top_k: int = 50, top_p: float = 1.0,
                               do_sample: bool = True, repetition_penalty: float = 1.05) -> Tuple[list, int]:
         self._require_type("voice_design", "Loaded model does not support voice design generation")
+        self._validate(language)
         return self._design_impl(text, instruct, language, non_streaming_mode, max_new_tokens, min_new_tokens,
                                  temperature, top_k, top_p, do_sample, repetition_penalty)
 
@@ -538,6 +559,7 @@ class FasterQwen3TTS:
                                         top_p: float = 1.0, do_sample: bool = True, repetition_penalty: float = 1.05,
                                         chunk_size: int = 12) -> Generator[Tuple[np.ndarray, int, dict], None, None]:
         self._require_type("voice_design", "Loaded model does not support voice design generation")
+        self._validate(language)
         m, talker, config, tie, tam, tth, tpe = self._simple(text, None, instruct, language, True, non_streaming_mode,
                                                               None)
         yield from self.stream_from_embeds(tie, tam, tth, tpe, ref_codes=None, chunk_size=chunk_size,

@@ -73,6 +73,19 @@ class SyntheticOuter:
         self.model = inner
         self.syn_cfg = None
 
+    # ---- request validation (upstream raises ValueError for names it does not know) ---------------------------
+    def _validate_languages(self, languages) -> None:
+        known = self.model.config.talker_config.codec_language_id
+        for lang in languages:
+            if lang is not None and lang.lower() != "auto" and lang.lower() not in known:
+                raise ValueError(f"Unsupported language: {lang}. Supported: {sorted(known)} or 'Auto'")
+
+    def _validate_speakers(self, speakers) -> None:
+        known = self.model.config.talker_config.spk_id
+        for spk in speakers:
+            if spk not in (None, "") and spk.lower() not in known:
+                raise ValueError(f"Unsupported speaker: {spk}. Supported: {sorted(known)}")
+
     # ---- chat template + tokenizer -------------------------------------------------------------------------
     @staticmethod
     def _build_assistant_text(text: str) -> str:

@@ -324,6 +324,29 @@ def gen_window(out_path):
             print(f"{name}: chunk lens {lens} decode calls (frames) {tok.calls}")
     finally:
         streaming_mod.fast_generate_streaming = real_stream
+    # non-streaming: generate_voice_clone's decode + reference trim (model.py:914-938)
+    gen_mod = sys.modules["fq3ref.generate"]
+    real_gen = gen_mod.fast_generate
+    try:
+        for name, (n_gen, n_ref, tk) in WC.NONSTREAM_CASES.items():
+            tok = WC.FakeTokenizer(**tk)
+            ref_codes = WC.ref_codes_for(n_ref)
+            gen_mod.fast_generate = lambda **kw: (WC.generated_codes(n_gen), dict(WC.TIMING))
+            fake = types.SimpleNamespace(
+                _reject_ggml_cached_reference_args=lambda **kw: None,
+                _resolve_non_streaming_mode=lambda v, default: default,
+                _prepare_generation=lambda **kw: (types.SimpleNamespace(speech_tokenizer=tok), None, None, None, None,
+                                                  None, None, ref_codes),
+                predictor_graph=None, talker_graph=None, sample_rate=WC.SR)
+            fn = ref_cls.generate_voice_clone
+            fn = getattr(fn, "__wrapped__", fn)
+            audio, sr = fn(fake, "text", "English", ref_audio="x.wav")
+            out[name + "_audio"] = np.asarray(audio[0], dtype=np.float32)
+            out[name + "_decoded_T"] = np.array(tok.calls, dtype=np.int64)
+            names.append(name)
+            print(f"{name}: {len(audio[0])} samples, decode calls {tok.calls}, sr {sr}")
+    finally:
+        gen_mod.fast_generate = real_gen
     out["names"] = np.array(names)
     np.savez_compressed(out_path, **out)
 

@@ -58,3 +58,22 @@ def ref_codes_for(n, seed=99):
     if not n:
         return None
     return torch.randint(0, 256, (n, 16), generator=torch.Generator().manual_seed(seed))
+
+
+# non-streaming decode + proportional reference trim (model.py:914-938): name -> (generated frames or None, reference
+# frames, tokenizer kwargs)
+NONSTREAM_CASES = {
+    "nonstream_icl": (37, 29, {}),
+    "nonstream_icl_short_decoder_numpy": (11, 40, {"short": 7, "as_numpy": True}),
+    "nonstream_xvec": (20, 0, {}),
+    "nonstream_no_tokens": (None, 12, {}),
+}
+
+
+def generated_codes(n, seed=5):
+    if n is None:
+        return None
+    return torch.randint(0, 256, (n, 16), generator=torch.Generator().manual_seed(seed + n))
+
+
+TIMING = dict(prefill_ms=3.0, decode_s=0.5, steps=10, ms_per_step=50.0, steps_per_s=20.0)

@@ -110,3 +110,39 @@ def test_wav_reader_without_soundfile(tts, tmp_path):
         w.writeframes((np.ones((1600, 2)) * 1000).astype("<i2").tobytes())
     audio, sr = tts._load_ref_audio_with_silence(p, silence_secs=0.5)
     assert sr == 16000 and audio.ndim == 1 and audio.shape[0] == 1600 + 8000 and float(audio[-1]) == 0.0
+
+
+def test_custom_voice_and_design_validate_like_the_reference(tts, monkeypatch):
+    """model.py:1155-1167,1343-1346: model type check, upstream language / speaker validators, 0.6B drops `instruct`;
+    the request never reaches the engine here (fast_generate is a double that records what it was handed)."""
+    import faster_qwen3_tts.generate as G
+    seen = {}
+
+    def fake_fast_generate(**kw):
+        seen["P"] = kw["talker_input_embeds"].shape[1]
+        return None, {}
+
+    monkeypatch.setattr(G, "fast_generate", fake_fast_generate)
+    with pytest.raises(ValueError, match="Unsupported speaker"):
+        tts.generate_custom_voice("hi", "zorg", "English")
+    with pytest.raises(ValueError, match="Unsupported language"):
+        tts.generate_custom_voice("hi", "Aiden", "Klingon")
+    with pytest.raises(ValueError, match="Unsupported language"):
+        tts.generate_voice_design("hi", "a calm voice", "Klingon")
+    audio, sr = tts.generate_custom_voice("hi there", "Aiden", "English", instruct="cheerful")
+    assert sr == tts.sample_rate and audio[0].shape == (1,)            # "no tokens" -> one zero sample (model.py:1199-1201)
+    p_with = seen["P"]
+    tts.model.model.tts_model_size = "0b6"
+    try:
+        tts.generate_custom_voice("hi there", "Aiden", "English", instruct="cheerful")
+    finally:
+        del tts.model.model.tts_model_size
+    assert seen["P"] < p_with                                          # the instruct turn was dropped
+    tts.model.model.tts_model_type = "base"
+    try:
+        with pytest.raises(ValueError, match="does not support custom voice"):
+            tts.generate_custom_voice("hi", "Aiden", "English")
+        with pytest.raises(ValueError, match="does not support voice design"):
+            tts.generate_voice_design("hi", "x", "English")
+    finally:
+        del tts.model.model.tts_model_type

@@ -36,3 +36,20 @@ def test_window_policy_reproduces_reference_chunks(tts, name):
     assert np.array_equal(audio, gold[name + "_audio"])              # sample for sample
     assert all(sr == WC.SR for _, sr, _ in got)
     assert [t["chunk_index"] for _, _, t in got] == list(range(len(sizes)))
+
+
+@pytest.mark.parametrize("name", sorted(WC.NONSTREAM_CASES))
+def test_non_streaming_decode_and_reference_trim(tts, name, monkeypatch):
+    """generate_voice_clone (model.py:895-951): ICL reference frames are prepended for the decode and cut off
+    proportionally afterwards; no tokens -> a single zero sample."""
+    import faster_qwen3_tts.generate as G
+    gold = np.load(GOLD)
+    n_gen, n_ref, tk = WC.NONSTREAM_CASES[name]
+    tok = WC.FakeTokenizer(**tk)
+    ref_codes = WC.ref_codes_for(n_ref)
+    monkeypatch.setattr(G, "fast_generate", lambda **kw: (WC.generated_codes(n_gen), dict(WC.TIMING)))
+    monkeypatch.setattr(tts, "_prepare_generation",
+                        lambda **kw: (types.SimpleNamespace(speech_tokenizer=tok), None, None, None, None, None, None, ref_codes))
+    audio, sr = tts.generate_voice_clone("text", "English", ref_audio="x.wav")
+    assert sr == WC.SR and tok.calls == gold[name + "_decoded_T"].tolist()
+    assert np.array_equal(np.asarray(audio[0], dtype=np.float32), gold[name + "_audio"])
