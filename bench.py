@@ -4,19 +4,29 @@
 Metric (BASELINE.json): xRealTime (RTF = audio seconds / wall seconds) and p50 TTFA, Qwen3-TTS-12Hz-1.7B streaming,
 chunk_size=8, on 1/2/4/8 B200 (independent replicas, no collective on this path).
 
-A "step" is one streaming request of SURVEY.md section 8(d) config 3: prompt P=232 (ICL-shaped), 128 frames (10.24 s of
-audio) generated in chunks of 8, every chunk decoded to 24 kHz PCM with the reference's two-phase window policy.
-min_new_tokens = max_new_tokens pins the work per step (EOS cannot cut a run short).  Weights are random-init at the
-real 1.7B geometry, inputs synthetic (no checkpoint / tokenizer exists offline).
+A "step" is one streaming voice-clone request of SURVEY.md section 8(d) config 3: an ICL prompt of P=232 positions
+(a 30-word reference transcript + a 17-word text + 174 reference codec frames = 13.9 s of reference audio, assembled
+by the package's own prompt builder), 128 frames (10.24 s of audio) generated in chunks of 8, every chunk decoded to
+24 kHz PCM with the reference's two-phase window policy.  min_new_tokens = max_new_tokens pins the work per step.
+Weights are random-init at the real 1.7B geometry, inputs synthetic (no checkpoint / tokenizer exists offline).
 
-  value  : RTF with prompt embeddings already resident in HBM, CUDA-event timed, max over ranks
-  e2e    : RTF through the public API (FasterQwen3TTS.generate_voice_clone_streaming) with prompt embeddings in
-           pinned HOST memory (H2D inside the timed region) and every PCM chunk read back to the host (D2H)
-  roofline: persistent decode kernel, algorithmic bytes per launch (SURVEY.md 8(d) B_alg) / CUDA-event launch time
-            against the MEASURED HBM copy bandwidth in MEASURED_PEAKS.json
-  cpu_baseline / --impl reference: the CPU oracle (torch eager, dynamic KV; the reference refuses non-CUDA devices,
-            model.py:181-182, and its arithmetic lives in absent third-party packages, so the oracle port IS its
-            CPU path) on a bounded sample of the same workload, all host threads.
+  value        RTF with the prompt embeddings already resident in HBM, CUDA-event timed, max over ranks
+  e2e          RTF through the public API FasterQwen3TTS.generate_voice_clone_streaming(text, language, ref_audio,
+               ref_text): tokenisation, voice-clone prompt, prompt assembly, prefill, decode, codec inside the timed
+               region; the reference audio is copied host->device from pinned memory every step (what the upstream
+               speaker / codec encoders would consume; those encoders themselves are absent offline and answered by
+               stand-ins) and every PCM chunk is read back to the host
+  roofline     persistent decode kernel, algorithmic bytes per launch (SURVEY.md 8(d) B_alg) / CUDA-event launch time
+               against the MEASURED HBM copy bandwidth in MEASURED_PEAKS.json
+  config4      BASELINE config 4 on the same GPU(s): `--batch` (32) concurrent requests per GPU decoded by the batched
+               persistent kernel (all requests share every pass over the weight tape), aggregate RTF with and without
+               the per-request codec decode, and its own roofline (weights once per step, KV per row)
+  gpu_reference the reference's METHOD (static KV + mask table + CUDA graphs + per-frame eager glue,
+               baseline/reference_method.py) on the same GPU, same synthetic weights, same request -- the stand-in
+               SURVEY 8(d)(ii) prescribes because upstream qwen_tts cannot be installed offline
+  cpu_baseline / --impl reference: the CPU oracle (torch eager fp32, dynamic KV) on a bounded sample, host threads
+  --sweep      chunk (BASELINE config 5: chunk_size in {1,2,4,8,16}) / prompt (TTFA over P in {10,40,96,232} split
+               into prefill, first chunk, first window) ; --size 0.6B = config 2
 """
 from __future__ import annotations
 
@@ -34,11 +44,12 @@ for p in (ROOT, os.path.join(ROOT, "faster-qwen3-tts_b200"), os.path.join(ROOT, 
     if p not in sys.path:
         sys.path.insert(0, p)
 
-os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the single JSON line (NCCL is only used for the timing barrier)
 import torch  # noqa: E402
 
 FRAME_S = 0.08  # 1920 samples @ 24 kHz (ggml_backend.py:22)
 METRIC = "xRealTime (RTF) Qwen3-TTS-1.7B streaming chunk_size=8 (p50 TTFA in config)"
+WORDS = ("the quick brown fox jumps over a lazy dog and then runs far away into the deep green forest where nobody "
+         "can find it again").split()
 
 
 def parse():
@@ -49,12 +60,16 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--size", default="1.7B", choices=["1.7B", "0.6B"])
     ap.add_argument("--prompt", type=int, default=232)
-    ap.add_argument("--trailing", type=int, default=25)
     ap.add_argument("--frames", type=int, default=128)
     ap.add_argument("--chunk", type=int, default=8)
-    ap.add_argument("--ref-frames", type=int, default=174, help="ICL reference codes prepended in codec Phase 1")
+    ap.add_argument("--ref-frames", type=int, default=174, help="ICL reference codec frames (13.9 s of reference audio)")
     ap.add_argument("--no-codec", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-reference", action="store_true")
+    ap.add_argument("--batch", type=int, default=32, help="config 4: concurrent requests per GPU (0/1 disables the leg)")
+    ap.add_argument("--batch-prompt", type=int, default=40)
+    ap.add_argument("--batch-steps", type=int, default=2)
+    ap.add_argument("--sweep", default="none", choices=["none", "chunk", "prompt", "all"])
     ap.add_argument("--num-ctas", type=int, default=0)
     ap.add_argument("--cpu-frames", type=int, default=64)
     return ap.parse_args()
@@ -104,15 +119,13 @@ class Clocks:
 # ----------------------------------------------------------------------------------------------------------------
 def cpu_oracle_run(args, frames: int):
     """prefill(P) + `frames` decode frames on the CPU oracle (fp32 eager -- torch CPU bf16 GEMV is ~50x slower than
-    fp32 on this host, measured 479 s for the same sample -- dynamic KV, all host threads).
-    Returns (rtf, seconds, threads, description)."""
+    fp32 on this host -- dynamic KV).  Returns (rtf, seconds, threads, description)."""
     from oracle import qwen3_tts_oracle as O
-    # torch-eager GEMV chains stop scaling (and collapse under OpenMP oversubscription: 479 s for this sample with 128
-    # threads on the GPU box vs 3 s with 8 threads) -- use at most 16 threads and report the number used
+    # torch-eager GEMV chains stop scaling (and collapse under OpenMP oversubscription) -- use at most 16 threads and
+    # report the number used
     nthreads = min(os.cpu_count() or 1, 16)
     torch.set_num_threads(nthreads)
     cfg = O.cfg_1p7b() if args.size == "1.7B" else O.cfg_0p6b()
-    # cheap deterministic weights (values do not matter for timing; shapes/dtype do)
     t0 = time.time()
     W = {}
     g = torch.Generator().manual_seed(0)
@@ -147,7 +160,7 @@ def cpu_oracle_run(args, frames: int):
         W["talker.code_predictor.small_to_mtp_projection.weight"] = fill((Hp, Ht), 0.02)
         W["talker.code_predictor.small_to_mtp_projection.bias"] = fill((Hp,), 0.02)
     om = O.OracleModel(cfg, W, max_pos=args.prompt + frames + 8)
-    tie, tth, tpe = O.make_inputs(cfg, args.prompt, args.trailing, seed=0, dtype=torch.float32)
+    tie, tth, tpe = O.make_inputs(cfg, args.prompt, 1, seed=0, dtype=torch.float32)
     import numpy as np
     u = np.random.default_rng(0).random((frames + 1, 16), dtype=np.float32)
     t_build = time.time() - t0
@@ -157,8 +170,9 @@ def cpu_oracle_run(args, frames: int):
                            max_seq_len=2048)
         dt = time.time() - t1
     n = int(codes.shape[0])
-    desc = (f"CPU oracle (torch eager fp32, dynamic KV): prefill P={args.prompt} + {n} frames of the {args.size} "
-            f"workload, {nthreads} threads, {dt:.1f}s (weights built in {t_build:.0f}s, untimed); no codec decode")
+    desc = (f"CPU oracle (torch eager FP32, dynamic KV): prefill P={args.prompt} + {n} frames of the {args.size} "
+            f"workload, {nthreads} threads, {dt:.1f}s (weights built in {t_build:.0f}s, untimed); NO codec decode, "
+            f"fp32 not bf16 -- a reported baseline on a bounded sample, not a like-for-like arm")
     return n * FRAME_S / dt, dt, nthreads, desc
 
 
@@ -180,17 +194,21 @@ def run_reference(args):
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": "x realtime", "n_gpus": args.gpus,
         "steps": len(vals), "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": workload_config(args, sample=f"prefill + {args.cpu_frames} frames per step"),
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, P=args.prompt, sample=f"prefill + {args.cpu_frames} frames per step, no codec decode",
+                                  same_config=False,
+                                  note="CPU oracle port in fp32 on <=16 host threads, ONE process whatever --gpus says: "
+                                       "a reported baseline, not the reference's CUDA-graph backend (see gpu_reference in "
+                                       "the b200 line for that method on the GPU)"),
         "cpu_baseline": {"value": v, "unit": "x realtime", "cores": nth, "kind": "port", "sample": desc},
         "e2e": {"value": v, "unit": "x realtime", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }))
 
 
-def workload_config(args, **extra):
-    c = {"workload": f"Qwen3-TTS-12Hz-{args.size} streaming voice-clone (SURVEY 8(d) config 3): prompt P={args.prompt}, "
-                     f"trailing text {args.trailing}, {args.frames} frames, chunk_size={args.chunk}, "
+def workload_config(args, P=None, **extra):
+    c = {"workload": f"Qwen3-TTS-12Hz-{args.size} streaming voice-clone (SURVEY 8(d) config 3): ICL prompt P={P or args.prompt} "
+                     f"({args.ref_frames} reference frames), {args.frames} frames, chunk_size={args.chunk}, "
                      f"T=0.9 top_k=50 top_p=1.0 penalty=1.05, min_new_tokens=max_new_tokens (fixed work)",
          "batch_per_gpu": 1, "parallelism": f"replicas x{args.gpus} (no collective)",
          "l2_policy": "per-step weight stream (3.2 GB tape) exceeds the 126 MB L2; no explicit flush needed"}
@@ -201,11 +219,31 @@ def workload_config(args, **extra):
 # ----------------------------------------------------------------------------------------------------------------
 # B200 arm
 # ----------------------------------------------------------------------------------------------------------------
+def craft_request(model, P_target: int, ref_frames: int):
+    """(text, ref_text, ref_audio, prepared tuple) whose ICL prompt (non_streaming_mode=True: text first, then the
+    reference frames, model.py:704-716) has exactly P_target positions when reachable."""
+    import numpy as np
+    ref_text = " ".join((WORDS * 3)[:30])
+    audio = (np.zeros(int(round(ref_frames / 12.5 * 24000)), dtype=np.float32), 24000)
+    best = None
+    for nw in range(2, 60):
+        text = " ".join((WORDS * 4)[:nw])
+        prep = model._prepare_generation(text, ref_audio=audio, ref_text=ref_text, language="English",
+                                         non_streaming_mode=True)
+        P = int(prep[3].shape[1])
+        if best is None or abs(P - P_target) < abs(best[0] - P_target):
+            best = (P, text, prep)
+        if P >= P_target:
+            break
+    P, text, prep = best
+    return text, ref_text, audio, prep, P
+
+
 def run_b200(args):
+    import numpy as np
     import torch.distributed as dist
     from faster_qwen3_tts import synthetic
     from faster_qwen3_tts.model import FasterQwen3TTS
-    from faster_qwen3_tts.streaming import fast_generate_streaming
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -215,29 +253,33 @@ def run_b200(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     cfg = synthetic.make_config(args.size)
+    B4 = args.batch if args.batch > 1 else 0
     model = FasterQwen3TTS.from_synthetic(args.size, device=f"cuda:{local}", dtype=torch.bfloat16, max_seq_len=2048,
-                                          seed=1234 + rank, num_ctas=args.num_ctas, with_codec=not args.no_codec)
+                                          seed=1234 + rank, num_ctas=args.num_ctas, with_codec=not args.no_codec,
+                                          max_batch=max(B4, 1))
     eng = model.engine
     eng.time_kernels = True
-    talker = model.model.model.talker
     tcfg = cfg.talker_config
-    tie, tam, tth, tpe = synthetic.make_prompt(cfg, args.prompt, args.trailing, seed=rank, dtype=torch.bfloat16, device=dev)
-    host_prompt = [t.cpu().pin_memory() for t in (tie, tth, tpe)]
-    ref_codes = None
-    if args.ref_frames > 0:
-        ref_codes = torch.randint(0, 2048, (args.ref_frames, 16), device=dev)
+    text, ref_text, ref_audio, prep, P = craft_request(model, args.prompt, args.ref_frames)
+    _, _, _, tie, tam, tth, tpe, ref_codes = prep
+    if args.no_codec:
+        ref_codes = None
+    pinned_audio = torch.from_numpy(ref_audio[0]).pin_memory()
     kw = dict(max_new_tokens=args.frames, min_new_tokens=args.frames, chunk_size=args.chunk)
-    launches0 = [0]
     chunk_ms, ttfa_ms = [], []
 
-    def step_resident(timed: bool):
+    def step_resident(timed: bool, chunk=None, prompt=None):
         """prompt resident in HBM; codes -> PCM per chunk on device.  Returns frames."""
         torch.manual_seed(rank * 1000 + len(ttfa_ms))
         e0 = torch.cuda.Event(enable_timing=True)
         e0.record()
         first = None
         n = 0
-        gen = model.stream_from_embeds(tie, tam, tth, tpe, ref_codes=ref_codes, to_host=False, **kw)
+        k2 = dict(kw)
+        if chunk is not None:
+            k2["chunk_size"] = chunk
+        a = prompt or (tie, tam, tth, tpe)
+        gen = model.stream_from_embeds(*a, ref_codes=ref_codes if prompt is None else None, to_host=False, **k2)
         for pcm, sr, t in gen:
             if first is None:
                 first = torch.cuda.Event(enable_timing=True)
@@ -251,18 +293,21 @@ def run_b200(args):
         return n
 
     def step_e2e():
-        """public API with HOST buffers: H2D of the prompt and D2H of every PCM chunk inside the timed region."""
+        """public API with HOST inputs: text + reference audio in, PCM chunks out (H2D / D2H inside the timed region)"""
         h2d = d2h = 0
-        d = [t.to(dev, non_blocking=True) for t in host_prompt]
-        h2d += sum(t.numel() * t.element_size() for t in host_prompt)
+        t0 = time.perf_counter()
+        a_dev = pinned_audio.to(dev, non_blocking=True)   # what the upstream speaker / codec encoders would read
+        h2d += pinned_audio.numel() * pinned_audio.element_size()
         n = 0
         t_first = None
-        t0 = time.perf_counter()
-        for pcm, sr, t in model.stream_from_embeds(d[0], tam, d[1], d[2], ref_codes=ref_codes, to_host=True, **kw):
+        for pcm, sr, t in model.generate_voice_clone_streaming(
+                text, "English", ref_audio=ref_audio, ref_text=ref_text, non_streaming_mode=True,
+                max_new_tokens=args.frames, min_new_tokens=args.frames, chunk_size=args.chunk):
             if t_first is None:
                 t_first = time.perf_counter() - t0
             d2h += pcm.nbytes
             n += t["chunk_steps"]
+        del a_dev
         return n, h2d, d2h, t_first
 
     def barrier():
@@ -287,20 +332,31 @@ def run_b200(args):
     ms = ev0.elapsed_time(ev1)
     launches = eng.launch_count + model.codec_launches() - l0
     clk = clocks.stop() if rank == 0 else None
-    # e2e leg
+    # ---- e2e leg
+    model._voice_prompt_cache.clear()
+    step_e2e()   # one untimed pass (lazy allocations of the prompt path)
     barrier()
     t0 = time.perf_counter()
     e_frames = h2d = d2h = 0
     e_ttfa = []
     for _ in range(args.steps):
+        model._voice_prompt_cache.clear()   # every step pays the voice-clone prompt, like a new speaker
         n, a, b, tf = step_e2e()
         e_frames += n
         h2d, d2h = a, b
         e_ttfa.append(tf * 1000)
     torch.cuda.synchronize()
     e_s = time.perf_counter() - t0
+    # ---- config 4: B concurrent requests per GPU through the batched kernel
+    c4 = None
+    if B4:
+        c4 = run_config4(args, model, cfg, dev, rank, barrier)
     from faster_qwen3_tts.replicas import aggregate
-    (ms, e_ms), (frames, e_frames) = aggregate([ms, e_s * 1000], [frames, e_frames], device=dev)
+    vals = [ms, e_s * 1000] + ([c4["ms_decode"], c4["ms_codec"]] if c4 else [])
+    cnts = [frames, e_frames] + ([c4["frames_decode"], c4["frames_codec"]] if c4 else [])
+    mx, sm = aggregate(vals, cnts, device=dev)
+    ms, e_ms = mx[0], mx[1]
+    frames, e_frames = sm[0], sm[1]
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -318,21 +374,24 @@ def run_b200(args):
     t_bytes, p_bytes = eng.tape_bytes()
     esz = 2
     Lt, nKV = tcfg.num_hidden_layers, tcfg.num_key_value_heads
-    pbar = args.prompt + (args.frames - 1) / 2.0
-    kv_bytes = Lt * 2 * nKV * 128 * esz * (pbar + 1)
-    # B_alg: every distinct weight byte once per frame; B_stream: bytes the tape actually streams
+    pbar = P + (args.frames - 1) / 2.0
+    kv_row = Lt * 2 * nKV * 128 * esz
+    kv_bytes = kv_row * (pbar + 1)
     from faster_qwen3_tts.weights import stack_config
     pc = stack_config(cfg.code_predictor_config)
     pred_layers = pc["num_hidden_layers"] * (2 * pc["hidden_size"] * (pc["num_attention_heads"] + pc["num_key_value_heads"]) * 128
                                              + 3 * pc["hidden_size"] * pc["intermediate_size"]) * esz
     pred_heads = 15 * pc["vocab_size"] * pc["hidden_size"] * esz
     mtp = (tcfg.hidden_size * pc["hidden_size"] * esz) if cfg.has_mtp else 0
-    b_alg = t_bytes + kv_bytes + pred_layers + pred_heads + mtp
+    w_alg = t_bytes + pred_layers + pred_heads + mtp      # every distinct weight byte once per frame
+    b_alg = w_alg + kv_bytes
     b_stream = t_bytes + kv_bytes + p_bytes
     k_ms = statistics.mean(chunk_ms) if chunk_ms else None
-    traffic = None
-    traffic_file = next((f for f in ("r1c_decode_kernel_ncu.csv", "r1b_decode_kernel_ncu.csv")
-                         if os.path.exists(os.path.join(ROOT, "profiles", f))), "r1b_decode_kernel_ncu.csv")
+    traffic, traffic_file = None, None
+    for f in ("r2_decode_kernel_ncu.csv", "r1c_decode_kernel_ncu.csv"):
+        if os.path.exists(os.path.join(ROOT, "profiles", f)):
+            traffic_file = f
+            break
     try:  # DRAM bytes of one launch from the committed ncu capture of this kernel (profiles/)
         for line in open(os.path.join(ROOT, "profiles", traffic_file)):
             f = line.strip().split(",")
@@ -340,8 +399,6 @@ def run_b200(args):
                 traffic = (traffic or 0.0) + float(f[3]) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[f[2]]
     except Exception:
         traffic = None
-    # the talker step alone (the kernel the north_star's HBM target is stated for): MODE_TALKER_STEP launches at the
-    # run's mean position, bytes = talker layer weights + KV(p) (no head), timed live with CUDA events
     talker = None
     try:
         ppos = int(pbar)
@@ -355,7 +412,7 @@ def run_b200(args):
             eng.talker_step(xh, ppos)
         t1e.record(); t1e.synchronize()
         ts_ms = t0e.elapsed_time(t1e) / 20
-        ts_bytes = t_bytes - tcfg.vocab_size * tcfg.hidden_size * esz + Lt * 2 * nKV * 128 * esz * (ppos + 1)
+        ts_bytes = t_bytes - tcfg.vocab_size * tcfg.hidden_size * esz + kv_row * (ppos + 1)
         talker = {"position": ppos, "ms": ts_ms, "bytes": ts_bytes, "achieved": ts_bytes / (ts_ms / 1000) / 1e9,
                   "frac": ts_bytes / (ts_ms / 1000) / 1e9 / peak,
                   "note": "one launch per step here (launch + pipeline fill included); inside the fused loop the step is shorter"}
@@ -364,9 +421,9 @@ def run_b200(args):
     roof = None
     if k_ms:
         ach = b_alg * args.chunk / (k_ms / 1000) / 1e9
-        roof = {"bound": "hbm", "kernel": "fq3_decode_kernel<bf16> (one launch = one 8-frame chunk)",
+        roof = {"bound": "hbm", "kernel": "fq3_decode_kernel<bf16> (one launch = one %d-frame chunk)" % args.chunk,
                 "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
-                "traffic_source": "ncu --set full capture of one 8-frame launch, profiles/" + traffic_file,
+                "traffic_source": ("ncu --set full capture of one 8-frame launch, profiles/" + traffic_file) if traffic_file else None,
                 "peak_source": peak_kind, "alg_bytes_per_frame": b_alg, "launch_ms": k_ms,
                 "streamed_bytes_per_frame": b_stream, "streamed_frac": b_stream * args.chunk / (k_ms / 1000) / 1e9 / peak,
                 "ms_per_frame": k_ms / args.chunk, "talker_step": talker}
@@ -374,12 +431,46 @@ def run_b200(args):
         "metric": METRIC, "value": value, "unit": "x realtime", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": workload_config(args, ttfa_ms_p50=statistics.median(ttfa_ms) if ttfa_ms else None,
+        "config": workload_config(args, P=P, ttfa_ms_p50=statistics.median(ttfa_ms) if ttfa_ms else None,
                                   ttfa_ms_e2e_p50=statistics.median(e_ttfa) if e_ttfa else None,
-                                  codec=not args.no_codec, ctas=eng.num_ctas, ref_frames=args.ref_frames),
+                                  codec=not args.no_codec, ctas=eng.num_ctas, ref_frames=args.ref_frames,
+                                  e2e_path="FasterQwen3TTS.generate_voice_clone_streaming(text, language, ref_audio, "
+                                           "ref_text, non_streaming_mode=True): tokeniser + voice prompt + prompt "
+                                           "assembly + prefill inside TTFA; speaker/codec ENCODERS are stand-ins"),
         "e2e": {"value": e2e, "unit": "x realtime", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": int(launches), "clocks": clk, "roofline": roof,
     }
+    if c4:
+        fd, fc = sm[2], sm[3]
+        md, mc = mx[2], mx[3]
+        kms = c4["kernel_ms"]
+        pb4 = c4["P"] + (args.frames - 1) / 2.0
+        bytes_step = w_alg + B4 * kv_row * (pb4 + 1)     # weights once per step, KV per row
+        ach4 = bytes_step * args.chunk / (kms / 1000) / 1e9 if kms else None
+        out["config4"] = {
+            "workload": f"BASELINE config 4: {B4} concurrent requests per GPU, P={c4['P']} (left-padded batch, mixed lengths "
+                        f"{c4['lens'][0]}..{c4['lens'][1]}), {args.frames} frames each, chunk_size={args.chunk}, independent "
+                        f"uniforms per request; batched persistent kernel (one launch per chunk for all requests)",
+            "requests_per_gpu": B4, "n_gpus": world,
+            "rtf_aggregate_decode": fd * FRAME_S / (md / 1000), "rtf_aggregate_with_codec": fc * FRAME_S / (mc / 1000) if mc else None,
+            "ms_per_frame_step": kms / args.chunk if kms else None,
+            "speedup_vs_batch1_decode": (fd * FRAME_S / (md / 1000)) / (value * 1.0) if value else None,
+            "roofline": {"bound": "hbm", "kernel": "fq3_decode_batch_kernel<bf16> (one launch = one chunk of all requests)",
+                         "achieved": ach4, "peak": peak, "unit": "GB/s", "frac": ach4 / peak if ach4 else None,
+                         "alg_bytes_per_step": bytes_step, "launch_ms": kms,
+                         "note": "weights once per step + KV of every row; frac measures HBM use, aggregate RTF the gain"},
+        }
+    if not args.no_gpu_reference and not args.no_codec:
+        try:
+            out["gpu_reference"] = run_gpu_reference(args, model, cfg, dev, (tie, tam, tth, tpe), ref_codes)
+            gr = out["gpu_reference"]
+            out["gpu_reference"]["engine_over_reference_method"] = {
+                "rtf": value / gr["rtf"] if gr.get("rtf") else None,
+                "ttfa": gr["ttfa_ms_p50"] / statistics.median(ttfa_ms) if gr.get("ttfa_ms_p50") and ttfa_ms else None}
+        except Exception as ex:
+            out["gpu_reference"] = {"error": repr(ex)[:300]}
+    if args.sweep != "none":
+        out["sweeps"] = run_sweeps(args, model, cfg, dev, step_resident, chunk_ms, ttfa_ms)
     if not args.no_cpu_baseline and world == 1:
         try:
             rtf, dt, nth, desc = cpu_oracle_run(args, args.cpu_frames)
@@ -390,6 +481,152 @@ def run_b200(args):
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_config4(args, model, cfg, dev, rank, barrier):
+    """B concurrent requests on this GPU: decode-only timing (CUDA events) and decode + per-request codec."""
+    from faster_qwen3_tts import synthetic
+    B = args.batch
+    H = cfg.talker_config.hidden_size
+    g = torch.Generator().manual_seed(77 + rank)
+    Pm = args.batch_prompt
+    lens = [int(x) for x in torch.randint(max(4, Pm - 12), Pm + 1, (B,), generator=g)]
+    lens[0] = Pm
+    tie = torch.zeros(B, Pm, H, dtype=torch.bfloat16)
+    tam = torch.zeros(B, Pm, dtype=torch.long)
+    for b, L in enumerate(lens):
+        tie[b, Pm - L:] = torch.randn(L, H, generator=g).to(torch.bfloat16)
+        tam[b, Pm - L:] = 1
+    tpe = torch.randn(H, generator=g).to(torch.bfloat16)
+    tth = tpe[None, None].expand(B, 1, H).contiguous()
+    tie, tam, tth, tpe = tie.to(dev), tam.to(dev), tth.to(dev), tpe[None, None].to(dev)
+    kw = dict(max_new_tokens=args.frames, min_new_tokens=args.frames, chunk_size=args.chunk)
+    eng = model.engine
+    kms = []
+
+    def run(decode_audio):
+        n = 0
+        for items in model.stream_batch_from_embeds(tie, tam, tth, tpe, to_host=False, decode_audio=decode_audio, **kw):
+            n += sum(t["chunk_steps"] for _, _, _, t in items)
+            if eng.last_kernel_ms is not None and not decode_audio:
+                kms.append(eng.last_kernel_ms)
+        return n
+
+    run(False)
+    kms.clear()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    fd = 0
+    for _ in range(args.batch_steps):
+        fd += run(False)
+    e1.record()
+    barrier()
+    ms_d = e0.elapsed_time(e1)
+    ms_c, fc = 0.0, 0
+    if not args.no_codec:
+        run(True)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.batch_steps):
+            fc += run(True)
+        e1.record()
+        barrier()
+        ms_c = e0.elapsed_time(e1)
+    return {"ms_decode": ms_d, "frames_decode": fd, "ms_codec": ms_c, "frames_codec": fc,
+            "kernel_ms": statistics.mean(kms) if kms else None, "P": Pm, "lens": (min(lens), max(lens))}
+
+
+def run_gpu_reference(args, model, cfg, dev, prompt, ref_codes):
+    """The reference's method (CUDA-graphed torch modules + eager glue) on the same weights, same request."""
+    from baseline.reference_method import build_reference_method, ref_generate_streaming
+    from faster_qwen3_tts.codec import SpeechTokenizer
+    m = model.model.model
+    talker = m.talker
+    tie, tam, tth, tpe = prompt
+    t0 = time.time()
+    pg, tg = build_reference_method(talker, cfg, device=str(dev), dtype=torch.bfloat16, max_seq_len=2048,
+                                    prefill_len=tie.shape[1])
+    capture_s = time.time() - t0
+    st = SpeechTokenizer(m.speech_tokenizer.decoder, backend="torch")   # upstream's own codec path: torch modules / cuDNN
+    kw = dict(max_new_tokens=args.frames, min_new_tokens=args.frames, chunk_size=args.chunk)
+
+    def one():
+        talker.rope_deltas = None
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        first = None
+        n = 0
+        chunks = ref_generate_streaming(talker, tie, tam, tth, tpe, m.config.talker_config, pg, tg, **kw)
+        for pcm, sr, t in model._stream_audio(chunks, st, ref_codes, args.chunk, to_host=False):
+            if first is None:
+                torch.cuda.synchronize()
+                first = time.perf_counter() - t0
+            n += t["chunk_steps"]
+        torch.cuda.synchronize()
+        return n, time.perf_counter() - t0, first
+
+    one()
+    res = [one() for _ in range(max(2, min(args.steps, 3)))]
+    n = sum(r[0] for r in res)
+    s = sum(r[1] for r in res)
+    del pg, tg
+    torch.cuda.empty_cache()
+    return {"label": "reference-method stand-in (synthetic weights): static KV + mask table + torch.cuda.CUDAGraph of the "
+                     "talker step and of the 15-pass predictor loop + the reference's per-frame eager glue + torch/cuDNN codec "
+                     "(baseline/reference_method.py restating talker_graph.py / predictor_graph.py / streaming.py)",
+            "rtf": n * FRAME_S / s, "ttfa_ms_p50": statistics.median(r[2] for r in res) * 1000,
+            "ms_per_frame": s / n * 1000, "runs": len(res), "graph_capture_s": capture_s}
+
+
+def run_sweeps(args, model, cfg, dev, step_resident, chunk_ms, ttfa_ms):
+    from faster_qwen3_tts import synthetic
+    out = {}
+    if args.sweep in ("chunk", "all"):   # BASELINE config 5 (benchmarks/chunk_sweep.py:24-99)
+        rows = []
+        for ch in (1, 2, 4, 8, 16):
+            step_resident(False, chunk=ch)
+            n0 = len(ttfa_ms)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            fr = sum(step_resident(True, chunk=ch) for _ in range(3))
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            rows.append({"chunk_size": ch, "rtf": fr * FRAME_S / dt, "ttfa_ms_p50": statistics.median(ttfa_ms[n0:])})
+        out["chunk"] = rows
+    if args.sweep in ("prompt", "all"):  # TTFA over P with its three terms (SURVEY 8(d))
+        eng = model.engine
+        rows = []
+        for P in (10, 40, 96, 232):
+            pr = synthetic.make_prompt(cfg, P, 25, seed=P, dtype=torch.bfloat16, device=dev)
+            step_resident(False, prompt=pr)
+            n0 = len(ttfa_ms)
+            for _ in range(5):
+                step_resident(True, prompt=pr)
+            # split: prefill / first chunk / first window, each timed alone with CUDA events
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+            from faster_qwen3_tts.generate import begin_fused
+            m = model.model.model
+            parts = []
+            for _ in range(5):
+                ev[0].record()
+                begin_fused(eng, m.talker, pr[0], pr[1], pr[2], pr[3], m.config.talker_config, model.predictor_graph,
+                            model.talker_graph, max_new_tokens=args.frames, min_new_tokens=args.frames, temperature=0.9,
+                            top_k=50, top_p=1.0, do_sample=True, repetition_penalty=1.05, uniforms=None)
+                ev[1].record()
+                codes, res = eng.decode_chunk(args.chunk)
+                ev[2].record()
+                if m.speech_tokenizer is not None:
+                    m.speech_tokenizer.decode({"audio_codes": codes.unsqueeze(0)})
+                ev[3].record()
+                ev[3].synchronize()
+                parts.append([ev[i].elapsed_time(ev[i + 1]) for i in range(3)])
+            med = [statistics.median(p[i] for p in parts) for i in range(3)]
+            rows.append({"P": P, "ttfa_ms_p50": statistics.median(ttfa_ms[n0:]), "prefill_ms": med[0],
+                         "first_chunk_ms": med[1], "first_window_ms": med[2]})
+        out["prompt"] = rows
+    return out
 
 
 if __name__ == "__main__":

@@ -69,6 +69,8 @@ struct StackDev {
   int npos;
 };
 
+struct SlotParams;  // fq3_decode_batch.cuh
+
 struct KParams {
   StackDev t, p;
   int mode, ncta, nseg, seg_mtp;
@@ -108,6 +110,12 @@ struct KParams {
   float* PART;                 // [nH][attn_split][PART_STRIDE] partial attention results (acc[128], max, sum)
   unsigned* attn_cnt;          // [nH] arrival counters of the splits (cleared with the barrier words every launch)
   int mma_tape;                // 1: bf16 tensor-core fragment layout, 0: fp32 row-chunk layout
+  // ---- batched decode (fq3_decode_batch.cuh): B request slots share one pass over the weight tape
+  int nslots;                  // columns of this launch (0: single-sequence kernel)
+  const SlotParams* sl;        // [nslots] per-column request state (device)
+  float *XB, *X1B, *QKVB, *LOGB;   // fp32 [MAXCOL][ldX] / [MAXCOL][ldX] / [MAXCOL][ldQKV] / [MAXB][VMAX]
+  void *XNB, *ATTB, *ACTB, *PINB;  // model dtype GEMV inputs [MAXCOL][ldX] / [ldATT] / [ldACT] / [HMAX]
+  int* TOKB;                   // [MAXB] cb0 token of every column after the talker sampling step
 };
 
 // ------------------------------------------------------------------------------------------------------------
@@ -204,6 +212,7 @@ struct __align__(128) Smem {
   volatile int stop_flag;   // consumers -> producer
   volatile int prod_done;   // producer -> consumers
   volatile int prod_issued; // tiles issued by the producer
+  int bst[5][32];           // batched kernel: replicated per-column loop state (token, step, gen_step, finished, emitted)
 };
 
 // All dynamic shared memory of the kernel is one Smem; going through this accessor (instead of a reference carried

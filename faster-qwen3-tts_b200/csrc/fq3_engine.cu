@@ -14,6 +14,7 @@
 
 #include "../../include/fq3_engine.h"
 #include "fq3_decode.cuh"
+#include "fq3_decode_batch.cuh"
 
 using namespace fq3;
 
@@ -33,6 +34,18 @@ static int fail(int code, const char* fmt, ...) {
       return fail(FQ3_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); \
   } while (0)
 
+// make the engine's device current for the duration of an ABI call and restore the caller's (torch's) device after
+struct DevGuard {
+  int prev = -1, dev;
+  explicit DevGuard(int d) : dev(d) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != dev) cudaSetDevice(dev);
+  }
+  ~DevGuard() {
+    if (prev >= 0 && prev != dev) cudaSetDevice(prev);
+  }
+};
+
 struct SegHost {
   int rows, K;
   uint64_t bytes;  // total tape bytes of this segment (all CTAs)
@@ -45,15 +58,33 @@ struct PackGrp {
   int32_t K;
 };
 
+// host-side record of one request slot (fq3_begin_request latches it; the kernels read it through KParams / SlotParams)
+struct SlotHost {
+  bool active = false;
+  int prefill_len = 0, rope_delta = 0, n_left_pad = 0, max_new = 0, min_new = 0, trailing_len = 0;
+  const void* trailing = nullptr;
+  const void* tts_pad = nullptr;
+  const float* uniforms = nullptr;
+  Sampling sp_t{1, 50, 0.9f, 1.0f, 1.05f}, sp_p{1, 50, 0.9f, 1.0f, 1.0f};
+};
+
 struct fq3_engine {
   fq3_config cfg;
   bool bf16;
   size_t esz;
   int ncta;
   int dev;
+  int max_batch = 1;
   bool loaded = false;
-  bool request_active = false;
-  // device buffers
+  std::vector<SlotHost> slots;
+  size_t tkv_slot = 0, pkv_slot = 0;   // bytes of one slot's K (or V) cache: talker / predictor
+  // batched decode: activation matrices + per-launch slot table
+  float *XB = nullptr, *X1B = nullptr, *QKVB = nullptr, *LOGB = nullptr;
+  void *XNB = nullptr, *ATTB = nullptr, *ACTB = nullptr, *PINB = nullptr;
+  int* TOKB = nullptr;
+  SlotParams* sl_dev = nullptr;
+  SlotParams* sl_host = nullptr;  // pinned
+  // device buffers (slot-major: slot s starts at s * <per-slot size>)
   void *t_kc = nullptr, *t_vc = nullptr, *p_kc = nullptr, *p_vc = nullptr;
   float *X = nullptr, *X1 = nullptr, *QKV = nullptr, *ATT = nullptr, *ACT = nullptr, *LOGITS = nullptr, *PART = nullptr;
   unsigned* bar = nullptr;
@@ -248,11 +279,15 @@ extern "C" int fq3_engine_create(const fq3_config* cfg, fq3_engine** out) {
   e->esz = e->bf16 ? 2 : 4;
   e->dev = cfg->device;
   e->ncta = cfg->num_ctas > 0 ? std::min(cfg->num_ctas, prop.multiProcessorCount) : prop.multiProcessorCount;
+  e->max_batch = cfg->max_batch > 0 ? cfg->max_batch : 1;
+  if (e->max_batch > MAXB) { delete e; return fail(FQ3_ERR_INVALID, "max_batch %d exceeds %d", cfg->max_batch, MAXB); }
   if (e->bf16) {
     CK(cudaFuncSetAttribute(fq3_decode_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes()));
+    CK(cudaFuncSetAttribute(fq3_decode_batch_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes()));
     CK(cudaFuncSetAttribute(sample_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes()));
   } else {
     CK(cudaFuncSetAttribute(fq3_decode_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes()));
+    CK(cudaFuncSetAttribute(fq3_decode_batch_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes()));
     CK(cudaFuncSetAttribute(sample_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes()));
   }
   int occ = 0;
@@ -261,12 +296,15 @@ extern "C" int fq3_engine_create(const fq3_config* cfg, fq3_engine** out) {
   if (occ < 1) { delete e; return fail(FQ3_ERR_INVALID, "decode kernel does not fit on an SM (smem %zu)", smem_bytes()); }
 
   const fq3_stack_config &T = cfg->talker, &Pc = cfg->predictor;
+  const int MB = e->max_batch;
+  e->slots.assign(MB, SlotHost());
   const size_t tkv = (size_t)T.num_hidden_layers * T.num_key_value_heads * cfg->max_seq_len * 128 * e->esz;
   const size_t pkv = (size_t)Pc.num_hidden_layers * Pc.num_key_value_heads * 32 * 128 * e->esz;
-  CK(cudaMalloc(&e->t_kc, tkv)); CK(cudaMalloc(&e->t_vc, tkv));
-  CK(cudaMalloc(&e->p_kc, pkv)); CK(cudaMalloc(&e->p_vc, pkv));
-  CK(cudaMemset(e->t_kc, 0, tkv)); CK(cudaMemset(e->t_vc, 0, tkv));
-  CK(cudaMemset(e->p_kc, 0, pkv)); CK(cudaMemset(e->p_vc, 0, pkv));
+  e->tkv_slot = tkv; e->pkv_slot = pkv;
+  CK(cudaMalloc(&e->t_kc, tkv * MB)); CK(cudaMalloc(&e->t_vc, tkv * MB));
+  CK(cudaMalloc(&e->p_kc, pkv * MB)); CK(cudaMalloc(&e->p_vc, pkv * MB));
+  CK(cudaMemset(e->t_kc, 0, tkv * MB)); CK(cudaMemset(e->t_vc, 0, tkv * MB));
+  CK(cudaMemset(e->p_kc, 0, pkv * MB)); CK(cudaMemset(e->p_vc, 0, pkv * MB));
   const int ldX = std::max(T.hidden_size, Pc.hidden_size);
   const int ldQKV = std::max((T.num_attention_heads + 2 * T.num_key_value_heads) * 128,
                              (Pc.num_attention_heads + 2 * Pc.num_key_value_heads) * 128);
@@ -277,10 +315,28 @@ extern "C" int fq3_engine_create(const fq3_config* cfg, fq3_engine** out) {
   CK(cudaMalloc(&e->ACT, 2 * ldACT * sizeof(float))); CK(cudaMalloc(&e->LOGITS, VMAX * sizeof(float)));
   CK(cudaMalloc(&e->bar, 32768)); CK(cudaMemset(e->bar, 0, 32768));
   CK(cudaMalloc(&e->PART, (size_t)T.num_attention_heads * 16 * PART_STRIDE * sizeof(float)));
-  CK(cudaMalloc(&e->state, 64)); CK(cudaMemset(e->state, 0, 64));
-  CK(cudaMallocHost(&e->state_host, 64));
-  CK(cudaMalloc(&e->past_hidden, HMAX * sizeof(float))); CK(cudaMemset(e->past_hidden, 0, HMAX * sizeof(float)));
-  CK(cudaMalloc(&e->seen, VMAX / 8)); CK(cudaMemset(e->seen, 0, VMAX / 8));
+  CK(cudaMalloc(&e->state, 32 * MB)); CK(cudaMemset(e->state, 0, 32 * MB));   // 8 ints per slot
+  CK(cudaMallocHost(&e->state_host, 32 * MB));
+  CK(cudaMalloc(&e->past_hidden, (size_t)MB * HMAX * sizeof(float))); CK(cudaMemset(e->past_hidden, 0, (size_t)MB * HMAX * sizeof(float)));
+  CK(cudaMalloc(&e->seen, (size_t)MB * (VMAX / 8))); CK(cudaMemset(e->seen, 0, (size_t)MB * (VMAX / 8)));
+  if (MB > 1) {
+    // batched decode: activation matrices [column][ld] (column = slot, predictor pass 0: token * B + slot)
+    auto zalloc = [&](void** p, size_t bytes) -> cudaError_t {
+      cudaError_t r = cudaMalloc(p, bytes);
+      return r != cudaSuccess ? r : cudaMemset(*p, 0, bytes);
+    };
+    CK(zalloc((void**)&e->XB, (size_t)MAXCOL * ldX * sizeof(float)));
+    CK(zalloc((void**)&e->X1B, (size_t)MAXCOL * ldX * sizeof(float)));
+    CK(zalloc((void**)&e->QKVB, (size_t)MAXCOL * ldQKV * sizeof(float)));
+    CK(zalloc((void**)&e->LOGB, (size_t)MAXB * VMAX * sizeof(float)));
+    CK(zalloc(&e->XNB, (size_t)MAXCOL * ldX * e->esz));
+    CK(zalloc(&e->ATTB, (size_t)MAXCOL * ldATT * e->esz));
+    CK(zalloc(&e->ACTB, (size_t)MAXCOL * ldACT * e->esz));
+    CK(zalloc(&e->PINB, (size_t)MAXCOL * HMAX * e->esz));
+    CK(zalloc((void**)&e->TOKB, MAXB * sizeof(int)));
+    CK(cudaMalloc(&e->sl_dev, MAXB * sizeof(SlotParams)));
+    CK(cudaMallocHost(&e->sl_host, MAXB * sizeof(SlotParams)));
+  }
   {
     const long long rec_t = 2LL * (T.num_attention_heads + 2 * T.num_key_value_heads) * 128 + 2LL * T.num_attention_heads * 128 + 4LL * T.hidden_size + 2LL * T.intermediate_size;
     const long long rec_p = 2LL * (Pc.num_attention_heads + 2 * Pc.num_key_value_heads) * 128 + 2LL * Pc.num_attention_heads * 128 + 4LL * Pc.hidden_size + 2LL * Pc.intermediate_size;
@@ -303,6 +359,9 @@ extern "C" int fq3_engine_create(const fq3_config* cfg, fq3_engine** out) {
   k.X = e->X; k.X1 = e->X1; k.QKV = e->QKV; k.ATT = e->ATT; k.ACT = e->ACT; k.LOGITS = e->LOGITS;
   k.ldX = ldX; k.ldQKV = ldQKV; k.ldATT = ldATT; k.ldACT = ldACT;
   k.bar = e->bar; k.state = e->state; k.past_hidden = e->past_hidden; k.seen = e->seen;
+  k.XB = e->XB; k.X1B = e->X1B; k.QKVB = e->QKVB; k.LOGB = e->LOGB;
+  k.XNB = e->XNB; k.ATTB = e->ATTB; k.ACTB = e->ACTB; k.PINB = e->PINB; k.TOKB = e->TOKB;
+  k.nslots = 0; k.sl = e->sl_dev;
   k.has_mtp = cfg->has_mtp_projection; k.ncb = cfg->num_code_groups - 1; k.eos = cfg->codec_eos_token_id;
   k.max_seq_len = cfg->max_seq_len;
   k.dbg = e->dbg; k.dbg_stride_layer = e->dbg_stride;
@@ -329,7 +388,8 @@ extern "C" void fq3_engine_destroy(fq3_engine* e) {
   if (!e) return;
   cudaSetDevice(e->dev);
   void* ptrs[] = {e->t_kc, e->t_vc, e->p_kc, e->p_vc, e->X, e->X1, e->QKV, e->ATT, e->ACT, e->LOGITS, e->PART, e->bar,
-                  e->state, e->past_hidden, e->seen, e->dbg, e->tape, e->grps, e->segtab, e->cta_grp_off};
+                  e->state, e->past_hidden, e->seen, e->dbg, e->tape, e->grps, e->segtab, e->cta_grp_off,
+                  e->XB, e->X1B, e->QKVB, e->LOGB, e->XNB, e->ATTB, e->ACTB, e->PINB, e->TOKB, e->sl_dev};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   for (auto& kv : e->tabs)
@@ -337,6 +397,7 @@ extern "C" void fq3_engine_destroy(fq3_engine* e) {
   for (void* p : e->pf_buf)
     if (p) cudaFree(p);
   if (e->state_host) cudaFreeHost(e->state_host);
+  if (e->sl_host) cudaFreeHost(e->sl_host);
   delete e;
 }
 
@@ -380,7 +441,7 @@ __global__ void mtp_table_kernel(const void* __restrict__ emb, const void* __res
 extern "C" int fq3_engine_load_weights(fq3_engine* e, const fq3_tensor* tensors, int32_t n, void* stream_) {
   if (!e || !tensors) return fail(FQ3_ERR_INVALID, "null argument");
   cudaStream_t stream = (cudaStream_t)stream_;
-  CK(cudaSetDevice(e->dev));
+  DevGuard dev_guard(e->dev);
   std::map<std::string, const fq3_tensor*> tm;
   for (int i = 0; i < n; ++i) tm[tensors[i].name] = &tensors[i];
   const fq3_config& cfg = e->cfg;
@@ -721,17 +782,45 @@ static Sampling to_sampling(const fq3_sampling* s) {
   return r;
 }
 
-extern "C" int fq3_import_kv(fq3_engine* e, int32_t layer, const void* k_dev, const void* v_dev, int32_t P, void* stream_) {
+static int check_slot(fq3_engine* e, int slot) {
+  if (slot < 0 || slot >= e->max_batch) return fail(FQ3_ERR_INVALID, "slot %d outside [0, max_batch=%d)", slot, e->max_batch);
+  return 0;
+}
+static void* slot_tk(fq3_engine* e, int s) { return (uint8_t*)e->t_kc + (size_t)s * e->tkv_slot; }
+static void* slot_tv(fq3_engine* e, int s) { return (uint8_t*)e->t_vc + (size_t)s * e->tkv_slot; }
+static void* slot_pk(fq3_engine* e, int s) { return (uint8_t*)e->p_kc + (size_t)s * e->pkv_slot; }
+static void* slot_pv(fq3_engine* e, int s) { return (uint8_t*)e->p_vc + (size_t)s * e->pkv_slot; }
+
+// kernel parameters of a single-sequence launch on slot s: the slot's caches / state + the request it latched
+static KParams kp_for_slot(fq3_engine* e, int s) {
+  KParams kp = e->kp;
+  const SlotHost& h = e->slots[s];
+  kp.t.kc = slot_tk(e, s); kp.t.vc = slot_tv(e, s); kp.p.kc = slot_pk(e, s); kp.p.vc = slot_pv(e, s);
+  kp.state = e->state + 8 * s;
+  kp.past_hidden = e->past_hidden + (size_t)s * HMAX;
+  kp.seen = e->seen + (size_t)s * (VMAX / 32);
+  kp.prefill_len = h.prefill_len; kp.rope_delta = h.rope_delta; kp.n_left_pad = h.n_left_pad;
+  kp.max_new = h.max_new; kp.min_new = h.min_new; kp.trailing_len = h.trailing_len;
+  kp.trailing = h.trailing; kp.tts_pad = h.tts_pad; kp.uniforms = h.uniforms;
+  kp.sp_t = h.sp_t; kp.sp_p = h.sp_p;
+  kp.nslots = 0;
+  return kp;
+}
+
+extern "C" int fq3_import_kv(fq3_engine* e, int32_t slot, int32_t layer, const void* k_dev, const void* v_dev, int32_t P,
+                             void* stream_) {
   if (!e || !k_dev || !v_dev) return fail(FQ3_ERR_INVALID, "null argument");
+  int rc;
+  if ((rc = check_slot(e, slot))) return rc;
   if (P > e->cfg.max_seq_len)
     return fail(FQ3_ERR_TOO_LONG, "Input is too long: prefill has %d tokens but max_seq_len=%d. Use shorter text or shorter reference audio.", P, e->cfg.max_seq_len);
   if (layer < 0 || layer >= e->cfg.talker.num_hidden_layers) return fail(FQ3_ERR_INVALID, "layer out of range");
-  CK(cudaSetDevice(e->dev));
+  DevGuard dev_guard(e->dev);
   cudaStream_t stream = (cudaStream_t)stream_;
   const int nKV = e->cfg.talker.num_key_value_heads, S = e->cfg.max_seq_len;
   const size_t row = (size_t)P * 128 * e->esz, pitch = (size_t)S * 128 * e->esz;
-  uint8_t* kd = (uint8_t*)e->t_kc + (size_t)layer * nKV * pitch;
-  uint8_t* vd = (uint8_t*)e->t_vc + (size_t)layer * nKV * pitch;
+  uint8_t* kd = (uint8_t*)slot_tk(e, slot) + (size_t)layer * nKV * pitch;
+  uint8_t* vd = (uint8_t*)slot_tv(e, slot) + (size_t)layer * nKV * pitch;
   if (P > 0) {
     CK(cudaMemcpy2DAsync(kd, pitch, k_dev, row, row, nKV, cudaMemcpyDeviceToDevice, stream));
     CK(cudaMemcpy2DAsync(vd, pitch, v_dev, row, row, nKV, cudaMemcpyDeviceToDevice, stream));
@@ -739,32 +828,58 @@ extern "C" int fq3_import_kv(fq3_engine* e, int32_t layer, const void* k_dev, co
   return 0;
 }
 
-extern "C" int fq3_set_generation_state(fq3_engine* e, int32_t n_left_pad, int32_t rope_delta) {
-  if (!e) return fail(FQ3_ERR_INVALID, "null argument");
-  e->kp.n_left_pad = n_left_pad;
-  e->kp.rope_delta = rope_delta;
+extern "C" int fq3_export_kv(fq3_engine* e, int32_t slot, int32_t layer, void* k_dev, void* v_dev, int32_t P, void* stream_) {
+  if (!e || !k_dev || !v_dev) return fail(FQ3_ERR_INVALID, "null argument");
+  int rc;
+  if ((rc = check_slot(e, slot))) return rc;
+  if (P < 0 || P > e->cfg.max_seq_len) return fail(FQ3_ERR_INVALID, "P outside the cache");
+  if (layer < 0 || layer >= e->cfg.talker.num_hidden_layers) return fail(FQ3_ERR_INVALID, "layer out of range");
+  DevGuard dev_guard(e->dev);
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const int nKV = e->cfg.talker.num_key_value_heads, S = e->cfg.max_seq_len;
+  const size_t row = (size_t)P * 128 * e->esz, pitch = (size_t)S * 128 * e->esz;
+  const uint8_t* ks = (const uint8_t*)slot_tk(e, slot) + (size_t)layer * nKV * pitch;
+  const uint8_t* vs = (const uint8_t*)slot_tv(e, slot) + (size_t)layer * nKV * pitch;
+  if (P > 0) {
+    CK(cudaMemcpy2DAsync(k_dev, row, ks, pitch, row, nKV, cudaMemcpyDeviceToDevice, stream));
+    CK(cudaMemcpy2DAsync(v_dev, row, vs, pitch, row, nKV, cudaMemcpyDeviceToDevice, stream));
+  }
   return 0;
 }
 
-extern "C" int fq3_talker_step(fq3_engine* e, const void* embeds_dev, int32_t position, void* hidden_out_dev, void* stream_) {
+extern "C" int fq3_set_generation_state(fq3_engine* e, int32_t slot, int32_t n_left_pad, int32_t rope_delta) {
+  if (!e) return fail(FQ3_ERR_INVALID, "null argument");
+  int rc;
+  if ((rc = check_slot(e, slot))) return rc;
+  e->slots[slot].n_left_pad = n_left_pad;
+  e->slots[slot].rope_delta = rope_delta;
+  return 0;
+}
+
+extern "C" int fq3_talker_step(fq3_engine* e, int32_t slot, const void* embeds_dev, int32_t position, void* hidden_out_dev,
+                               void* stream_) {
   if (!e || !embeds_dev || !hidden_out_dev) return fail(FQ3_ERR_INVALID, "null argument");
   if (!e->loaded) return fail(FQ3_ERR_STATE, "weights not loaded");
+  int rc;
+  if ((rc = check_slot(e, slot))) return rc;
   if (position < 0 || position >= e->cfg.max_seq_len) return fail(FQ3_ERR_INVALID, "position %d outside the cache", position);
-  CK(cudaSetDevice(e->dev));
-  KParams kp = e->kp;
+  DevGuard dev_guard(e->dev);
+  KParams kp = kp_for_slot(e, slot);
   kp.mode = MODE_TALKER_STEP;
   kp.in_embeds = embeds_dev; kp.hidden_out = hidden_out_dev; kp.position = position;
   kp.dbg_on = e->dbg_on;
   return launch_decode(e, kp, (cudaStream_t)stream_);
 }
 
-extern "C" int fq3_predictor_run(fq3_engine* e, const void* pred_input_dev, const fq3_sampling* sp, const float* uniforms_dev,
-                                 int64_t* codes_out_dev, void* stream_) {
+extern "C" int fq3_predictor_run(fq3_engine* e, int32_t slot, const void* pred_input_dev, const fq3_sampling* sp,
+                                 const float* uniforms_dev, int64_t* codes_out_dev, void* stream_) {
   if (!e || !pred_input_dev || !sp || !codes_out_dev) return fail(FQ3_ERR_INVALID, "null argument");
   if (!e->loaded) return fail(FQ3_ERR_STATE, "weights not loaded");
+  int rc;
+  if ((rc = check_slot(e, slot))) return rc;
   if (sp->do_sample && !uniforms_dev) return fail(FQ3_ERR_INVALID, "do_sample needs uniforms");
-  CK(cudaSetDevice(e->dev));
-  KParams kp = e->kp;
+  DevGuard dev_guard(e->dev);
+  KParams kp = kp_for_slot(e, slot);
   kp.mode = MODE_PRED_RUN;
   kp.pred_input = pred_input_dev; kp.pred_uniforms = uniforms_dev; kp.codes_out = (long long*)codes_out_dev;
   kp.sp_p = to_sampling(sp);
@@ -777,7 +892,7 @@ extern "C" int fq3_sample_logits(fq3_engine* e, const void* logits_dev, int32_t 
                                  int32_t suppress_eos, int64_t* token_out_dev, void* stream_) {
   if (!e || !logits_dev || !sp || !token_out_dev) return fail(FQ3_ERR_INVALID, "null argument");
   if (V <= 0 || V > VMAX) return fail(FQ3_ERR_INVALID, "V out of range");
-  CK(cudaSetDevice(e->dev));
+  DevGuard dev_guard(e->dev);
   cudaStream_t stream = (cudaStream_t)stream_;
   const Sampling s = to_sampling(sp);
   if (e->bf16)
@@ -789,59 +904,120 @@ extern "C" int fq3_sample_logits(fq3_engine* e, const void* logits_dev, int32_t 
   return 0;
 }
 
-extern "C" int fq3_begin_request(fq3_engine* e, const fq3_request* rq, const void* past_hidden_dev, const void* trailing_text_dev,
-                                 const void* tts_pad_dev, const float* uniforms_dev, const fq3_sampling* sp_talker,
-                                 const fq3_sampling* sp_predictor, void* stream_) {
+extern "C" int fq3_begin_request(fq3_engine* e, int32_t slot, const fq3_request* rq, const void* past_hidden_dev,
+                                 const void* trailing_text_dev, const void* tts_pad_dev, const float* uniforms_dev,
+                                 const fq3_sampling* sp_talker, const fq3_sampling* sp_predictor, void* stream_) {
   if (!e || !rq || !past_hidden_dev || !tts_pad_dev || !sp_talker || !sp_predictor) return fail(FQ3_ERR_INVALID, "null argument");
   if (!e->loaded) return fail(FQ3_ERR_STATE, "weights not loaded");
+  int rc;
+  if ((rc = check_slot(e, slot))) return rc;
   if (rq->prefill_len > e->cfg.max_seq_len)
     return fail(FQ3_ERR_TOO_LONG, "Input is too long: prefill has %d tokens but max_seq_len=%d. Use shorter text or shorter reference audio.", rq->prefill_len, e->cfg.max_seq_len);
   if ((sp_talker->do_sample || sp_predictor->do_sample) && !uniforms_dev) return fail(FQ3_ERR_INVALID, "sampling needs uniforms");
   if (rq->trailing_len > 0 && !trailing_text_dev) return fail(FQ3_ERR_INVALID, "trailing_len > 0 but no trailing text");
   if (rq->first_token < 0 || rq->first_token >= e->cfg.talker.vocab_size) return fail(FQ3_ERR_INVALID, "first_token out of range");
-  CK(cudaSetDevice(e->dev));
+  DevGuard dev_guard(e->dev);
   cudaStream_t stream = (cudaStream_t)stream_;
-  KParams& k = e->kp;
-  k.prefill_len = rq->prefill_len; k.rope_delta = rq->rope_delta; k.n_left_pad = rq->n_left_pad;
-  k.max_new = rq->max_new_tokens; k.min_new = rq->min_new_tokens; k.trailing_len = rq->trailing_len;
-  k.trailing = trailing_text_dev; k.tts_pad = tts_pad_dev; k.uniforms = uniforms_dev;
-  k.sp_t = to_sampling(sp_talker); k.sp_p = to_sampling(sp_predictor);
-  if (e->bf16) set_state_kernel<true><<<4, 256, 0, stream>>>(e->state, e->past_hidden, e->seen, past_hidden_dev, e->cfg.talker.hidden_size, rq->first_token, rq->gen_step);
-  else set_state_kernel<false><<<4, 256, 0, stream>>>(e->state, e->past_hidden, e->seen, past_hidden_dev, e->cfg.talker.hidden_size, rq->first_token, rq->gen_step);
+  SlotHost& h = e->slots[slot];
+  h.prefill_len = rq->prefill_len; h.rope_delta = rq->rope_delta; h.n_left_pad = rq->n_left_pad;
+  h.max_new = rq->max_new_tokens; h.min_new = rq->min_new_tokens; h.trailing_len = rq->trailing_len;
+  h.trailing = trailing_text_dev; h.tts_pad = tts_pad_dev; h.uniforms = uniforms_dev;
+  h.sp_t = to_sampling(sp_talker); h.sp_p = to_sampling(sp_predictor);
+  int* st = e->state + 8 * slot;
+  float* ph = e->past_hidden + (size_t)slot * HMAX;
+  uint32_t* seen = e->seen + (size_t)slot * (VMAX / 32);
+  if (e->bf16) set_state_kernel<true><<<4, 256, 0, stream>>>(st, ph, seen, past_hidden_dev, e->cfg.talker.hidden_size, rq->first_token, rq->gen_step);
+  else set_state_kernel<false><<<4, 256, 0, stream>>>(st, ph, seen, past_hidden_dev, e->cfg.talker.hidden_size, rq->first_token, rq->gen_step);
   e->launches++;
   CK(cudaGetLastError());
-  e->request_active = true;
+  h.active = true;
   return 0;
 }
 
-extern "C" int fq3_decode_chunk(fq3_engine* e, int32_t n_frames, int64_t* codes_out_dev, fq3_chunk_result* res, void* stream_) {
-  if (!e || !codes_out_dev || !res) return fail(FQ3_ERR_INVALID, "null argument");
-  if (!e->request_active) return fail(FQ3_ERR_STATE, "fq3_begin_request has not been called");
-  if (n_frames <= 0) return fail(FQ3_ERR_INVALID, "n_frames must be positive");
-  CK(cudaSetDevice(e->dev));
-  cudaStream_t stream = (cudaStream_t)stream_;
+// batched launch: slots[0..n) become the columns of one pass over the weight tape
+static int launch_decode_batch(fq3_engine* e, const int32_t* slots, int n, int n_frames, long long* codes_out_dev,
+                               cudaStream_t stream) {
+  if (!e->sl_dev) return fail(FQ3_ERR_STATE, "engine was created with max_batch = 1");
+  if (n > e->ncta) return fail(FQ3_ERR_INVALID, "%d slots need at least as many CTAs (engine has %d)", n, e->ncta);
+  if (e->cfg.has_mtp_projection && !e->kp.mtp_tab)
+    return fail(FQ3_ERR_STATE, "batched decode needs the tabulated predictor input projection (unset FQ3_NO_MTP_TABLE)");
+  for (int j = 0; j < n; ++j) {
+    const int s = slots[j];
+    const SlotHost& h = e->slots[s];
+    SlotParams& p = e->sl_host[j];
+    p.kc = slot_tk(e, s); p.vc = slot_tv(e, s); p.pkc = slot_pk(e, s); p.pvc = slot_pv(e, s);
+    p.state = e->state + 8 * s;
+    p.past_hidden = e->past_hidden + (size_t)s * HMAX;
+    p.seen = e->seen + (size_t)s * (VMAX / 32);
+    p.trailing = h.trailing; p.tts_pad = h.tts_pad; p.uniforms = h.uniforms;
+    p.codes_out = codes_out_dev + (size_t)j * n_frames * 16;
+    p.prefill_len = h.prefill_len; p.rope_delta = h.rope_delta; p.n_left_pad = h.n_left_pad;
+    p.max_new = h.max_new; p.min_new = h.min_new; p.trailing_len = h.trailing_len;
+    p.sp_t = h.sp_t; p.sp_p = h.sp_p;
+  }
+  CK(cudaMemcpyAsync(e->sl_dev, e->sl_host, (size_t)n * sizeof(SlotParams), cudaMemcpyHostToDevice, stream));
+  CK(cudaMemsetAsync(e->bar, 0, 32768, stream));
   KParams kp = e->kp;
   kp.mode = MODE_FUSED;
+  kp.nslots = n;
+  kp.sl = e->sl_dev;
   kp.n_frames = n_frames;
-  kp.codes_out = (long long*)codes_out_dev;
-  kp.dbg_on = e->dbg_on & 2;   // timing probes only; layer dumps belong to the step-wise entry points
-  int rc = launch_decode(e, kp, stream);
-  if (rc) return rc;
-  CK(cudaMemcpyAsync(e->state_host, e->state, 32, cudaMemcpyDeviceToHost, stream));
-  CK(cudaStreamSynchronize(stream));
-  res->next_token = e->state_host[0];
-  res->total_frames = e->state_host[1];
-  res->finished = e->state_host[3];
-  res->frames_emitted = e->state_host[4];
+  kp.dbg_on = 0;
+  void* args[] = {(void*)&kp};
+  if (e->bf16)
+    CK(cudaLaunchCooperativeKernel((const void*)fq3_decode_batch_kernel<true>, dim3(e->ncta), dim3(NTHREADS), args, smem_bytes(), stream));
+  else
+    CK(cudaLaunchCooperativeKernel((const void*)fq3_decode_batch_kernel<false>, dim3(e->ncta), dim3(NTHREADS), args, smem_bytes(), stream));
+  e->launches++;
   return 0;
 }
 
-extern "C" int fq3_get_past_hidden(fq3_engine* e, void* dst_dev, void* stream_) {
-  if (!e || !dst_dev) return fail(FQ3_ERR_INVALID, "null argument");
-  CK(cudaSetDevice(e->dev));
+extern "C" int fq3_decode_chunk(fq3_engine* e, const int32_t* slots, int32_t n_slots, int32_t n_frames,
+                                int64_t* codes_out_dev, fq3_chunk_result* res, void* stream_) {
+  if (!e || !slots || !codes_out_dev || !res) return fail(FQ3_ERR_INVALID, "null argument");
+  if (n_slots <= 0 || n_slots > e->max_batch) return fail(FQ3_ERR_INVALID, "n_slots %d outside [1, max_batch=%d]", n_slots, e->max_batch);
+  if (n_frames <= 0) return fail(FQ3_ERR_INVALID, "n_frames must be positive");
+  int rc;
+  for (int j = 0; j < n_slots; ++j) {
+    if ((rc = check_slot(e, slots[j]))) return rc;
+    if (!e->slots[slots[j]].active) return fail(FQ3_ERR_STATE, "fq3_begin_request has not been called for slot %d", slots[j]);
+    for (int i = 0; i < j; ++i)
+      if (slots[i] == slots[j]) return fail(FQ3_ERR_INVALID, "slot %d listed twice", slots[j]);
+  }
+  DevGuard dev_guard(e->dev);
   cudaStream_t stream = (cudaStream_t)stream_;
-  if (e->bf16) get_hidden_kernel<true><<<4, 256, 0, stream>>>(e->past_hidden, dst_dev, e->cfg.talker.hidden_size);
-  else get_hidden_kernel<false><<<4, 256, 0, stream>>>(e->past_hidden, dst_dev, e->cfg.talker.hidden_size);
+  if (n_slots == 1) {
+    KParams kp = kp_for_slot(e, slots[0]);
+    kp.mode = MODE_FUSED;
+    kp.n_frames = n_frames;
+    kp.codes_out = (long long*)codes_out_dev;
+    kp.dbg_on = e->dbg_on & 2;   // timing probes only; layer dumps belong to the step-wise entry points
+    if ((rc = launch_decode(e, kp, stream))) return rc;
+  } else {
+    if ((rc = launch_decode_batch(e, slots, n_slots, n_frames, (long long*)codes_out_dev, stream))) return rc;
+  }
+  for (int j = 0; j < n_slots; ++j)
+    CK(cudaMemcpyAsync(e->state_host + 8 * j, e->state + 8 * slots[j], 32, cudaMemcpyDeviceToHost, stream));
+  CK(cudaStreamSynchronize(stream));
+  for (int j = 0; j < n_slots; ++j) {
+    const int* st = e->state_host + 8 * j;
+    res[j].next_token = st[0];
+    res[j].total_frames = st[1];
+    res[j].finished = st[3];
+    res[j].frames_emitted = st[4];
+  }
+  return 0;
+}
+
+extern "C" int fq3_get_past_hidden(fq3_engine* e, int32_t slot, void* dst_dev, void* stream_) {
+  if (!e || !dst_dev) return fail(FQ3_ERR_INVALID, "null argument");
+  int rc;
+  if ((rc = check_slot(e, slot))) return rc;
+  DevGuard dev_guard(e->dev);
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const float* ph = e->past_hidden + (size_t)slot * HMAX;
+  if (e->bf16) get_hidden_kernel<true><<<4, 256, 0, stream>>>(ph, dst_dev, e->cfg.talker.hidden_size);
+  else get_hidden_kernel<false><<<4, 256, 0, stream>>>(ph, dst_dev, e->cfg.talker.hidden_size);
   e->launches++;
   CK(cudaGetLastError());
   return 0;
@@ -849,7 +1025,7 @@ extern "C" int fq3_get_past_hidden(fq3_engine* e, void* dst_dev, void* stream_) 
 
 extern "C" int fq3_barrier_test(fq3_engine* e, int32_t n, int32_t kind, void* stream_) {
   if (!e || !e->loaded) return fail(FQ3_ERR_STATE, "weights not loaded");
-  CK(cudaSetDevice(e->dev));
+  DevGuard dev_guard(e->dev);
   KParams kp = e->kp;
   kp.mode = MODE_BARRIER_TEST;
   kp.n_frames = n;
@@ -866,7 +1042,7 @@ extern "C" int fq3_debug_enable(fq3_engine* e, int32_t on) {
 extern "C" int fq3_debug_read(fq3_engine* e, int64_t offset, int64_t count, float* host_dst) {
   if (!e || !host_dst) return fail(FQ3_ERR_INVALID, "null argument");
   if (offset < 0 || count < 0 || (size_t)(offset + count) > e->dbg_floats) return fail(FQ3_ERR_INVALID, "debug range outside the buffer (%zu floats)", e->dbg_floats);
-  CK(cudaSetDevice(e->dev));
+  DevGuard dev_guard(e->dev);
   CK(cudaDeviceSynchronize());
   CK(cudaMemcpy(host_dst, e->dbg + offset, (size_t)count * sizeof(float), cudaMemcpyDeviceToHost));
   return 0;
@@ -882,6 +1058,7 @@ extern "C" int fq3_tape_bytes(fq3_engine* e, int64_t* talker_step_bytes, int64_t
 extern "C" int fq3_num_ctas(fq3_engine* e) { return e ? e->ncta : 0; }
 extern "C" int64_t fq3_launch_count(fq3_engine* e) { return e ? e->launches : 0; }
 extern "C" const char* fq3_last_error(void) { return g_err; }
-extern "C" const char* fq3_version(void) { return "fq3-b200 0.1.0 (sm_100a)"; }
+extern "C" int fq3_max_batch(fq3_engine* e) { return e ? e->max_batch : 0; }
+extern "C" const char* fq3_version(void) { return "fq3-b200 0.2.0 (sm_100a)"; }
 
 #include "fq3_prefill.cuh"

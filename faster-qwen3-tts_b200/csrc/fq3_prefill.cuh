@@ -197,7 +197,7 @@ extern "C" int fq3_engine_set_prefill_weights(fq3_engine* e, const fq3_tensor* t
     if (!*w.dst) return fail(FQ3_ERR_INVALID, "missing prefill tensor '%s'", w.nm);
   }
   if (H > 2048 || H % 32 || I % 32) return fail(FQ3_ERR_INVALID, "prefill geometry unsupported");
-  CK(cudaSetDevice(e->dev));
+  DevGuard dev_guard(e->dev);
   CK(cudaFuncSetAttribute(fq3gemm::conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fq3gemm::CONV_SMEM));
   const size_t S = e->cfg.max_seq_len;
   const size_t wide = std::max<size_t>(qd + 2 * kd, (size_t)I);
@@ -208,20 +208,26 @@ extern "C" int fq3_engine_set_prefill_weights(fq3_engine* e, const fq3_tensor* t
     CK(cudaMalloc(&e->pf_buf[3], S * wide * 2));   // qkv / act
     CK(cudaMalloc(&e->pf_buf[4], S * qd * 2));     // attention out
   }
+  // per FUNCTION, not per engine: size it for the largest cache any engine may have (SEQMAX), so a second engine
+  // with a shorter max_seq_len cannot lower the limit under the first one
   CK(cudaFuncSetAttribute(pf::attn_prefill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                          (int)((8 * ((S + 31) & ~31) + 8 * 128) * sizeof(float))));
+                          (int)((8 * (size_t)fq3::SEQMAX + 8 * 128) * sizeof(float))));
   e->pf_ready = true;
   return 0;
 }
 
-extern "C" int fq3_prefill(fq3_engine* e, const void* embeds_dev, int32_t P, int32_t n_left_pad, void* logits_out_dev,
-                           void* hidden_out_dev, void* stream_) {
+extern "C" int fq3_prefill(fq3_engine* e, int32_t slot, const void* embeds_dev, int32_t P, int32_t n_left_pad,
+                           void* logits_out_dev, void* hidden_out_dev, void* stream_) {
   if (!e || !embeds_dev || !logits_out_dev || !hidden_out_dev) return fail(FQ3_ERR_INVALID, "null argument");
+  {
+    int rcs;
+    if ((rcs = check_slot(e, slot))) return rcs;
+  }
   if (!e->pf_ready) return fail(FQ3_ERR_STATE, "fq3_engine_set_prefill_weights has not been called");
   if (P <= 0) return fail(FQ3_ERR_INVALID, "empty prompt");
   if (P > e->cfg.max_seq_len)
     return fail(FQ3_ERR_TOO_LONG, "Input is too long: prefill has %d tokens but max_seq_len=%d. Use shorter text or shorter reference audio.", P, e->cfg.max_seq_len);
-  CK(cudaSetDevice(e->dev));
+  DevGuard dev_guard(e->dev);
   cudaStream_t stream = (cudaStream_t)stream_;
   const fq3_stack_config& T = e->cfg.talker;
   const int L = T.num_hidden_layers, H = T.hidden_size, I = T.intermediate_size;
@@ -245,12 +251,12 @@ extern "C" int fq3_prefill(fq3_engine* e, const void* embeds_dev, int32_t P, int
       const int warps = P * (nH + 2 * nKV);
       pf::rope_kv_kernel<<<(warps * 32 + 255) / 256, 256, 0, stream>>>(
           wide, P, nH, nKV, (const bf*)k.t.qnorm + (size_t)l * 128, (const bf*)k.t.knorm + (size_t)l * 128, k.t.cos,
-          k.t.sin, k.t.npos, n_left_pad, T.rms_norm_eps, (bf*)e->t_kc + (size_t)l * nKV * S * 128,
-          (bf*)e->t_vc + (size_t)l * nKV * S * 128, S);
+          k.t.sin, k.t.npos, n_left_pad, T.rms_norm_eps, (bf*)slot_tk(e, slot) + (size_t)l * nKV * S * 128,
+          (bf*)slot_tv(e, slot) + (size_t)l * nKV * S * 128, S);
       e->launches++;
     }
     pf::attn_prefill_kernel<<<dim3((P + 7) / 8, nH), 256, attn_smem, stream>>>(
-        wide, P, nH, nKV, (const bf*)e->t_kc + (size_t)l * nKV * S * 128, (const bf*)e->t_vc + (size_t)l * nKV * S * 128, S,
+        wide, P, nH, nKV, (const bf*)slot_tk(e, slot) + (size_t)l * nKV * S * 128, (const bf*)slot_tv(e, slot) + (size_t)l * nKV * S * 128, S,
         n_left_pad, att);
     e->launches++;
     if ((rc = pf_gemm(e, att, (const bf*)e->pf_o + (size_t)l * H * qd, x, x1, P, qd, H, 0, stream))) return rc;

@@ -34,7 +34,7 @@ class Config(C.Structure):
     _fields_ = [("dtype", C.c_int32), ("device", C.c_int32), ("max_seq_len", C.c_int32),
                 ("num_code_groups", C.c_int32), ("codec_eos_token_id", C.c_int32),
                 ("has_mtp_projection", C.c_int32), ("num_ctas", C.c_int32), ("rope_positions", C.c_int32),
-                ("talker", StackConfig), ("predictor", StackConfig)]
+                ("talker", StackConfig), ("predictor", StackConfig), ("max_batch", C.c_int32)]
 
 
 class Tensor(C.Structure):
@@ -58,10 +58,11 @@ class ChunkResult(C.Structure):
 
 
 EXPORTS = [
-    "fq3_engine_create", "fq3_engine_load_weights", "fq3_engine_destroy", "fq3_import_kv",
+    "fq3_engine_create", "fq3_engine_load_weights", "fq3_engine_destroy", "fq3_import_kv", "fq3_export_kv",
     "fq3_set_generation_state", "fq3_talker_step", "fq3_predictor_run", "fq3_sample_logits", "fq3_begin_request",
     "fq3_decode_chunk", "fq3_get_past_hidden", "fq3_debug_enable", "fq3_debug_read", "fq3_tape_bytes",
-    "fq3_num_ctas", "fq3_launch_count", "fq3_last_error", "fq3_version", "fq3_barrier_test", "fq3_engine_set_prefill_weights", "fq3_prefill", "fq3_set_gemm_backend",
+    "fq3_num_ctas", "fq3_launch_count", "fq3_last_error", "fq3_version", "fq3_barrier_test",
+    "fq3_engine_set_prefill_weights", "fq3_prefill", "fq3_set_gemm_backend", "fq3_max_batch",
     "fq3_codec_create", "fq3_codec_load_weights", "fq3_codec_decode", "fq3_codec_flops", "fq3_codec_launch_count",
     "fq3_codec_destroy", "fq3_codec_last_error",
 ]
@@ -102,16 +103,20 @@ def load_library() -> C.CDLL:
     lib.fq3_engine_load_weights.argtypes = [C.c_void_p, C.POINTER(Tensor), C.c_int32, C.c_void_p]
     lib.fq3_engine_destroy.argtypes = [C.c_void_p]
     lib.fq3_engine_destroy.restype = None
-    lib.fq3_import_kv.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
-    lib.fq3_set_generation_state.argtypes = [C.c_void_p, C.c_int32, C.c_int32]
-    lib.fq3_talker_step.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
-    lib.fq3_predictor_run.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(Sampling), C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.fq3_import_kv.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
+    lib.fq3_export_kv.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
+    lib.fq3_set_generation_state.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32]
+    lib.fq3_talker_step.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
+    lib.fq3_predictor_run.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.POINTER(Sampling), C.c_void_p, C.c_void_p,
+                                      C.c_void_p]
     lib.fq3_sample_logits.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(Sampling), C.c_float, C.c_void_p,
                                       C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
-    lib.fq3_begin_request.argtypes = [C.c_void_p, C.POINTER(Request), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
-                                      C.POINTER(Sampling), C.POINTER(Sampling), C.c_void_p]
-    lib.fq3_decode_chunk.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.POINTER(ChunkResult), C.c_void_p]
-    lib.fq3_get_past_hidden.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.fq3_begin_request.argtypes = [C.c_void_p, C.c_int32, C.POINTER(Request), C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.c_void_p, C.POINTER(Sampling), C.POINTER(Sampling), C.c_void_p]
+    lib.fq3_decode_chunk.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.c_int32, C.c_int32, C.c_void_p,
+                                     C.POINTER(ChunkResult), C.c_void_p]
+    lib.fq3_get_past_hidden.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
+    lib.fq3_max_batch.argtypes = [C.c_void_p]
     lib.fq3_debug_enable.argtypes = [C.c_void_p, C.c_int32]
     lib.fq3_debug_read.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]
     lib.fq3_tape_bytes.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
@@ -119,7 +124,8 @@ def load_library() -> C.CDLL:
     lib.fq3_barrier_test.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
     lib.fq3_set_gemm_backend.argtypes = [C.c_int32]
     lib.fq3_engine_set_prefill_weights.argtypes = [C.c_void_p, C.POINTER(Tensor), C.c_int32]
-    lib.fq3_prefill.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.fq3_prefill.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
+                                C.c_void_p]
     lib.fq3_codec_create.argtypes = [C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_void_p)]
     lib.fq3_codec_destroy.argtypes = [C.c_void_p]
     lib.fq3_codec_destroy.restype = None
@@ -169,7 +175,7 @@ class Engine:
 
     def __init__(self, *, talker: dict, predictor: dict, dtype: torch.dtype, device="cuda", max_seq_len: int = 2048,
                  num_code_groups: int = 16, codec_eos_token_id: int = 2150, has_mtp_projection: bool = True,
-                 num_ctas: int = 0, rope_positions: Optional[int] = None):
+                 num_ctas: int = 0, rope_positions: Optional[int] = None, max_batch: int = 1):
         if not torch.cuda.is_available():
             raise RuntimeError("fq3 engine needs a CUDA device (sm_100a); no CPU fallback exists")
         self.lib = load_library()
@@ -191,12 +197,13 @@ class Engine:
 
         cfg = Config(FQ3_BF16 if dtype == torch.bfloat16 else FQ3_F32, self.device.index, self.max_seq_len,
                      num_code_groups, codec_eos_token_id, int(bool(has_mtp_projection)), int(num_ctas),
-                     self.rope_positions, sc(talker), sc(predictor))
+                     self.rope_positions, sc(talker), sc(predictor), int(max_batch))
+        self.max_batch = int(max_batch)
         h = C.c_void_p()
         _check(self.lib, self.lib.fq3_engine_create(C.byref(cfg), C.byref(h)))
         self.h = h
         self.H = talker["hidden_size"]
-        self._keep = {}  # tensors borrowed by the engine for the duration of a request
+        self._keep = {}  # slot -> tensors borrowed by the engine for the duration of that slot's request
         self.loaded = False
         self.has_prefill = False
         self._prefill_keep = None
@@ -242,34 +249,46 @@ class Engine:
         self._prefill_keep = keep
         self.has_prefill = True
 
-    def prefill(self, embeds: torch.Tensor, n_left_pad: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
-        """embeds [P,H] -> (logits [V], past_hidden [H]); KV slots [0,P) are written in the engine cache."""
+    def prefill(self, embeds: torch.Tensor, n_left_pad: int = 0, slot: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
+        """embeds [P,H] -> (logits [V], past_hidden [H]); cache rows [0,P) of request slot `slot` are written."""
         x = self._t(embeds.reshape(-1, self.H))
         logits = torch.empty(self.talker_cfg["vocab_size"], dtype=self.dtype, device=self.device)
         hidden = torch.empty(self.H, dtype=self.dtype, device=self.device)
-        _check(self.lib, self.lib.fq3_prefill(self.h, x.data_ptr(), x.shape[0], int(n_left_pad), logits.data_ptr(),
+        _check(self.lib, self.lib.fq3_prefill(self.h, int(slot), x.data_ptr(), x.shape[0], int(n_left_pad), logits.data_ptr(),
                                               hidden.data_ptr(), self._stream()))
         return logits, hidden
 
     # -- duck-type path ----------------------------------------------------------------------------------
-    def import_kv(self, layer: int, k: torch.Tensor, v: torch.Tensor):
+    def import_kv(self, layer: int, k: torch.Tensor, v: torch.Tensor, slot: int = 0):
         """k, v: [1, n_kv, P, 128] (HF cache layout) or [n_kv, P, 128]."""
         k, v = self._t(k.reshape(-1, k.shape[-2], k.shape[-1])), self._t(v.reshape(-1, v.shape[-2], v.shape[-1]))
-        _check(self.lib, self.lib.fq3_import_kv(self.h, layer, k.data_ptr(), v.data_ptr(), k.shape[1], self._stream()))
+        _check(self.lib, self.lib.fq3_import_kv(self.h, int(slot), layer, k.data_ptr(), v.data_ptr(), k.shape[1],
+                                                self._stream()))
         return k.shape[1]
 
-    def set_generation_state(self, n_left_pad: int, rope_delta: int):
-        _check(self.lib, self.lib.fq3_set_generation_state(self.h, int(n_left_pad), int(rope_delta)))
+    def export_kv(self, layer: int, P: int, slot: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
+        """cache rows [0,P) of one layer as (k, v) [n_kv, P, 128]"""
+        nkv = self.talker_cfg["num_key_value_heads"]
+        k = torch.empty(nkv, P, 128, dtype=self.dtype, device=self.device)
+        v = torch.empty_like(k)
+        _check(self.lib, self.lib.fq3_export_kv(self.h, int(slot), int(layer), k.data_ptr(), v.data_ptr(), int(P),
+                                                self._stream()))
+        return k, v
 
-    def talker_step(self, embeds: torch.Tensor, position: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    def set_generation_state(self, n_left_pad: int, rope_delta: int, slot: int = 0):
+        _check(self.lib, self.lib.fq3_set_generation_state(self.h, int(slot), int(n_left_pad), int(rope_delta)))
+
+    def talker_step(self, embeds: torch.Tensor, position: int, out: Optional[torch.Tensor] = None,
+                    slot: int = 0) -> torch.Tensor:
         x = self._t(embeds.reshape(-1))
         if out is None:
             out = torch.empty(self.H, dtype=self.dtype, device=self.device)
-        _check(self.lib, self.lib.fq3_talker_step(self.h, x.data_ptr(), int(position), out.data_ptr(), self._stream()))
+        _check(self.lib, self.lib.fq3_talker_step(self.h, int(slot), x.data_ptr(), int(position), out.data_ptr(),
+                                                  self._stream()))
         return out
 
     def predictor_run(self, pred_input: torch.Tensor, sp: SamplingParams,
-                      uniforms: Optional[torch.Tensor] = None) -> torch.Tensor:
+                      uniforms: Optional[torch.Tensor] = None, slot: int = 0) -> torch.Tensor:
         x = self._t(pred_input.reshape(2, -1))
         out = torch.empty(self.num_code_groups - 1, dtype=torch.long, device=self.device)
         u = None
@@ -278,7 +297,7 @@ class Engine:
                 uniforms = torch.rand(self.num_code_groups - 1, device=self.device)
             u = self._t(uniforms, torch.float32)
         s = sp.c()
-        _check(self.lib, self.lib.fq3_predictor_run(self.h, x.data_ptr(), C.byref(s), u.data_ptr() if u is not None else None,
+        _check(self.lib, self.lib.fq3_predictor_run(self.h, int(slot), x.data_ptr(), C.byref(s), u.data_ptr() if u is not None else None,
                                                      out.data_ptr(), self._stream()))
         return out
 
@@ -299,7 +318,7 @@ class Engine:
     def begin_request(self, *, first_token: int, prefill_len: int, gen_step: int, past_hidden: torch.Tensor,
                       trailing_text: torch.Tensor, tts_pad: torch.Tensor, max_new_tokens: int, min_new_tokens: int,
                       sp_talker: SamplingParams, sp_predictor: SamplingParams, uniforms: Optional[torch.Tensor],
-                      rope_delta: int = 0, n_left_pad: int = 0):
+                      rope_delta: int = 0, n_left_pad: int = 0, slot: int = 0):
         ph = self._t(past_hidden.reshape(-1))
         tt = self._t(trailing_text.reshape(-1, self.H)) if trailing_text is not None and trailing_text.numel() else None
         tp = self._t(tts_pad.reshape(-1))
@@ -309,31 +328,52 @@ class Engine:
         u = self._t(uniforms, torch.float32) if uniforms is not None else None
         if u is not None and u.numel() < (max_new_tokens + 1) * 16:
             raise ValueError("uniforms must have (max_new_tokens + 1) * 16 elements")
-        self._keep = dict(ph=ph, tt=tt, tp=tp, u=u)
+        self._keep[int(slot)] = dict(ph=ph, tt=tt, tp=tp, u=u)
         rq = Request(int(first_token), int(prefill_len), int(gen_step), int(rope_delta), int(n_left_pad),
                      int(max_new_tokens), int(min_new_tokens), 0 if tt is None else tt.shape[0])
         st, spd = sp_talker.c(), sp_predictor.c()
         _check(self.lib, self.lib.fq3_begin_request(
-            self.h, C.byref(rq), ph.data_ptr(), tt.data_ptr() if tt is not None else None, tp.data_ptr(),
+            self.h, int(slot), C.byref(rq), ph.data_ptr(), tt.data_ptr() if tt is not None else None, tp.data_ptr(),
             u.data_ptr() if u is not None else None, C.byref(st), C.byref(spd), self._stream()))
 
-    def decode_chunk(self, n_frames: int, out: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, ChunkResult]:
+    def decode_chunk(self, n_frames: int, out: Optional[torch.Tensor] = None, slot: int = 0) -> Tuple[torch.Tensor, ChunkResult]:
+        """Single-sequence launch on one slot: (codes [frames_emitted,16], result)."""
         if out is None:
             out = torch.empty(n_frames, 16, dtype=torch.long, device=self.device)
         res = ChunkResult()
+        sl = (C.c_int32 * 1)(int(slot))
         if self.time_kernels:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-        _check(self.lib, self.lib.fq3_decode_chunk(self.h, int(n_frames), out.data_ptr(), C.byref(res), self._stream()))
+        _check(self.lib, self.lib.fq3_decode_chunk(self.h, sl, 1, int(n_frames), out.data_ptr(), C.byref(res), self._stream()))
         if self.time_kernels:
             e1.record()
             e1.synchronize()
             self.last_kernel_ms = e0.elapsed_time(e1)
         return out[: res.frames_emitted], res
 
-    def past_hidden(self) -> torch.Tensor:
+    def decode_chunk_batch(self, slots, n_frames: int, out: Optional[torch.Tensor] = None):
+        """All listed slots advance up to n_frames frames in ONE launch sharing every pass over the weights.
+        Returns (codes [n_slots, n_frames, 16] -- row j valid up to results[j].frames_emitted --, [ChunkResult])."""
+        slots = [int(x) for x in slots]
+        n = len(slots)
+        if out is None:
+            out = torch.empty(n, n_frames, 16, dtype=torch.long, device=self.device)
+        res = (ChunkResult * n)()
+        sl = (C.c_int32 * n)(*slots)
+        if self.time_kernels:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        _check(self.lib, self.lib.fq3_decode_chunk(self.h, sl, n, int(n_frames), out.data_ptr(), res, self._stream()))
+        if self.time_kernels:
+            e1.record()
+            e1.synchronize()
+            self.last_kernel_ms = e0.elapsed_time(e1)
+        return out, list(res)
+
+    def past_hidden(self, slot: int = 0) -> torch.Tensor:
         out = torch.empty(self.H, dtype=self.dtype, device=self.device)
-        _check(self.lib, self.lib.fq3_get_past_hidden(self.h, out.data_ptr(), self._stream()))
+        _check(self.lib, self.lib.fq3_get_past_hidden(self.h, int(slot), out.data_ptr(), self._stream()))
         return out
 
     # -- introspection ----------------------------------------------------------------------------------------

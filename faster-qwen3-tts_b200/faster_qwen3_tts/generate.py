@@ -38,15 +38,17 @@ def _prefill(talker, tie, tam, tth, tpe):
 
 
 def begin_fused(engine, talker, tie, tam, tth, tpe, config, predictor_graph, talker_graph, *, max_new_tokens,
-                min_new_tokens, temperature, top_k, top_p, do_sample, repetition_penalty, uniforms):
-    """Prefill + first token + request latch (generate.py:104-140).  Returns the first token id."""
+                min_new_tokens, temperature, top_k, top_p, do_sample, repetition_penalty, uniforms, slot=None):
+    """Prefill + first token + request latch (generate.py:104-140) for ONE row [1,P,H] into request slot `slot`
+    (default: the slot the graph handles drive).  Returns the first token id."""
     eos_id = config.codec_eos_token_id
+    slot = int(getattr(talker_graph, "slot", 0) if slot is None else slot)
     native = getattr(engine, "has_prefill", False) and getattr(talker_graph, "use_native_prefill", True) \
         and tie.shape[0] == 1
+    pad = int((tam[0] == 0).sum().item()) if tam is not None else 0
     if native:
         # K3: hand-written prefill writes the KV cache directly (no talker.forward, no prefill_kv copies)
-        pad = int((tam[0] == 0).sum().item()) if tam is not None else 0
-        lg, ph = engine.prefill(tie[0], pad)
+        lg, ph = engine.prefill(tie[0], pad, slot=slot)
         import types
         out = types.SimpleNamespace(logits=lg.view(1, 1, -1), past_hidden=ph.view(1, 1, -1), generation_step=0,
                                     past_key_values=None)
@@ -61,16 +63,23 @@ def begin_fused(engine, talker, tie, tam, tth, tpe, config, predictor_graph, tal
                                  suppress_special=True, eos_id=eos_id, suppress_eos=min_new_tokens > 0)
     if native:
         prefill_len = int(tie.shape[1])
-        talker_graph.prefill_len = prefill_len
-        talker_graph.set_generation_state(tam, torch.tensor([-pad]) if pad else None)
+        n_left_pad, rope_delta = pad, -pad   # rotary position = cache index - pad count (talker_graph.py:210-211)
     else:
-        prefill_len = talker_graph.prefill_kv(out.past_key_values)
-        talker_graph.set_generation_state(tam, getattr(talker, "rope_deltas", None))
+        prefill_len = 0
+        for li in range(talker_graph.num_layers):
+            k, v = out.past_key_values[li]
+            prefill_len = engine.import_kv(li, k, v, slot=slot)
+        rd = getattr(talker, "rope_deltas", None)
+        n_left_pad = pad
+        rope_delta = int(round(float(rd.reshape(-1)[0].item()))) if rd is not None else 0
+    engine.set_generation_state(n_left_pad, rope_delta, slot=slot)
+    if slot == getattr(talker_graph, "slot", 0):
+        talker_graph.prefill_len, talker_graph.n_left_pad, talker_graph.rope_delta = prefill_len, n_left_pad, rope_delta
     gen_step = int(out.generation_step) if out.generation_step is not None else 0
     engine.begin_request(first_token=int(first.item()), prefill_len=prefill_len, gen_step=gen_step,
                          past_hidden=out.past_hidden, trailing_text=tth, tts_pad=tpe, max_new_tokens=max_new_tokens,
                          min_new_tokens=min_new_tokens, sp_talker=sp_t, sp_predictor=predictor_graph.sampling(),
-                         uniforms=uniforms, rope_delta=talker_graph.rope_delta, n_left_pad=talker_graph.n_left_pad)
+                         uniforms=uniforms, rope_delta=rope_delta, n_left_pad=n_left_pad, slot=slot)
     return first
 
 
@@ -161,7 +170,7 @@ def fast_generate(
         t1 = time.time()
         parts = []
         while True:
-            codes, res = engine.decode_chunk(_MAX_LAUNCH_FRAMES)
+            codes, res = engine.decode_chunk(_MAX_LAUNCH_FRAMES, slot=getattr(talker_graph, "slot", 0))
             if res.frames_emitted:
                 parts.append(codes.clone())
             if res.finished:

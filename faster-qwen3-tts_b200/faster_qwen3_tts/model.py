@@ -28,6 +28,45 @@ logger = logging.getLogger(__name__)
 CONTEXT_FRAMES = 25  # model.py:1056
 
 
+class _StreamWindow:
+    """Per-request state of the streaming codec-window policy (model.py:1052-1135), push-style so that several
+    requests of a batch can each keep their own window while their code chunks arrive interleaved."""
+
+    def __init__(self, owner, speech_tokenizer, ref_codes, chunk_size, to_host=True):
+        self.st, self.ref_codes = speech_tokenizer, ref_codes
+        self.min_cal = max(CONTEXT_FRAMES, chunk_size)
+        self.all_codes, self.prev_len, self.spf = [], 0, None
+        self.conv = owner._to_numpy if to_host else (lambda a: a.flatten())
+
+    def push(self, codec_chunk):
+        self.all_codes.append(codec_chunk)
+        n_new = codec_chunk.shape[0]
+        flat = torch.cat(self.all_codes, dim=0)
+        n_total = flat.shape[0]
+        ref_codes = self.ref_codes
+        if self.spf is None:
+            inp = torch.cat([ref_codes.to(flat.device), flat], dim=0) if ref_codes is not None else flat
+            audio_list, sr = self.st.decode({"audio_codes": inp.unsqueeze(0)})
+            audio = self.conv(audio_list[0])
+            if ref_codes is not None:
+                cut = int(ref_codes.shape[0] / max(inp.shape[0], 1) * len(audio))
+                gen_audio = audio[cut:]
+            else:
+                gen_audio = audio
+            new_audio = gen_audio[self.prev_len:]
+            self.prev_len = len(gen_audio)
+            if n_total >= self.min_cal:
+                self.spf = len(gen_audio) / n_total
+        else:
+            start = max(0, n_total - n_new - CONTEXT_FRAMES)
+            window = flat[start:]
+            n_ctx = window.shape[0] - n_new
+            audio_list, sr = self.st.decode({"audio_codes": window.unsqueeze(0)})
+            audio = self.conv(audio_list[0])
+            new_audio = audio[int(round(n_ctx * self.spf)):] if n_ctx > 0 else audio
+        return new_audio, sr
+
+
 class FasterQwen3TTS:
     def __init__(self, base_model, predictor_graph, talker_graph, device: str = "cuda",
                  dtype: torch.dtype = torch.bfloat16, max_seq_len: int = 2048):
@@ -109,13 +148,14 @@ class FasterQwen3TTS:
         return cls._wrap(base, device, dtype, max_seq_len)
 
     @classmethod
-    def _wrap(cls, base_model, device, dtype, max_seq_len, num_ctas: int = 0):
+    def _wrap(cls, base_model, device, dtype, max_seq_len, num_ctas: int = 0, max_batch: int = 1):
         from .predictor_graph import PredictorGraph
         from .talker_graph import TalkerGraph
         from .weights import engine_for_talker
         talker = base_model.model.talker
         tcfg = base_model.model.config.talker_config
-        engine = engine_for_talker(talker, dtype=dtype, device=device, max_seq_len=max_seq_len, num_ctas=num_ctas)
+        engine = engine_for_talker(talker, dtype=dtype, device=device, max_seq_len=max_seq_len, num_ctas=num_ctas,
+                                   max_batch=max_batch)
         pg = PredictorGraph(talker.code_predictor, talker.code_predictor.model.config, tcfg.hidden_size, device=device,
                             dtype=dtype, do_sample=True, top_k=50, temperature=0.9, engine=engine)
         tg = TalkerGraph(talker.model, tcfg, device=device, dtype=dtype, max_seq_len=max_seq_len, engine=engine)
@@ -124,7 +164,7 @@ class FasterQwen3TTS:
     @classmethod
     def from_synthetic(cls, size: str = "1.7B", device: str = "cuda", dtype: torch.dtype = torch.bfloat16,
                        max_seq_len: int = 2048, seed: int = 0, num_ctas: int = 0, with_codec: bool = True,
-                       codec_config=None):
+                       codec_config=None, max_batch: int = 1):
         """Random-init weights at the real geometry (no checkpoint exists offline)."""
         from . import synthetic
         from .codec import build_codec
@@ -136,7 +176,7 @@ class FasterQwen3TTS:
         st = build_codec(codec_config, seed=seed + 1, dtype=dtype, device=device) if with_codec else None
         base = synthetic.build_base_model(cfg, None, seed=seed, dtype=dtype, device=device, speech_tokenizer=st)
         base.syn_cfg = cfg
-        m = cls._wrap(base, device, dtype, max_seq_len, num_ctas=num_ctas)
+        m = cls._wrap(base, device, dtype, max_seq_len, num_ctas=num_ctas, max_batch=max_batch)
         return m
 
     def warmup(self, prefill_len: int = 100) -> None:
@@ -355,34 +395,9 @@ class FasterQwen3TTS:
         """The reference's hybrid streaming decode (model.py:1052-1135): Phase 1 re-decodes everything so far
         (reference codes prepended in ICL mode) until max(25, chunk_size) frames exist and calibrates
         samples_per_frame; Phase 2 decodes a 25-frame left-context window and trims the context."""
-        min_cal = max(CONTEXT_FRAMES, chunk_size)
-        all_codes, prev_len, spf = [], 0, None
-        conv = self._to_numpy if to_host else (lambda a: a.flatten())
+        win = _StreamWindow(self, speech_tokenizer, ref_codes, chunk_size, to_host)
         for codec_chunk, timing in chunks:
-            all_codes.append(codec_chunk)
-            n_new = codec_chunk.shape[0]
-            flat = torch.cat(all_codes, dim=0)
-            n_total = flat.shape[0]
-            if spf is None:
-                inp = torch.cat([ref_codes.to(flat.device), flat], dim=0) if ref_codes is not None else flat
-                audio_list, sr = speech_tokenizer.decode({"audio_codes": inp.unsqueeze(0)})
-                audio = conv(audio_list[0])
-                if ref_codes is not None:
-                    cut = int(ref_codes.shape[0] / max(inp.shape[0], 1) * len(audio))
-                    gen_audio = audio[cut:]
-                else:
-                    gen_audio = audio
-                new_audio = gen_audio[prev_len:]
-                prev_len = len(gen_audio)
-                if n_total >= min_cal:
-                    spf = len(gen_audio) / n_total
-            else:
-                start = max(0, n_total - n_new - CONTEXT_FRAMES)
-                window = flat[start:]
-                n_ctx = window.shape[0] - n_new
-                audio_list, sr = speech_tokenizer.decode({"audio_codes": window.unsqueeze(0)})
-                audio = conv(audio_list[0])
-                new_audio = audio[int(round(n_ctx * spf)):] if n_ctx > 0 else audio
+            new_audio, sr = win.push(codec_chunk)
             yield new_audio, sr, timing
 
     def _gen_kwargs(self, max_new_tokens, min_new_tokens, temperature, top_k, top_p, do_sample, repetition_penalty):
@@ -410,6 +425,75 @@ class FasterQwen3TTS:
                 yield (codes.cpu().numpy() if to_host else codes), self.sample_rate, timing
             return
         yield from self._stream_audio(chunks, st, ref_codes, chunk_size, to_host=to_host)
+
+    @torch.inference_mode()
+    def stream_batch_from_embeds(self, tie, tam, tth, tpe, ref_codes=None, chunk_size: int = 8, to_host: bool = True,
+                                 max_new_tokens: int = 2048, min_new_tokens: int = 2, temperature: float = 0.9,
+                                 top_k: int = 50, top_p: float = 1.0, do_sample: bool = True,
+                                 repetition_penalty: float = 1.05, uniforms=None, decode_audio: bool = True):
+        """Batched streaming from the point where the (left-padded) prompt batch exists (the tuple
+        ``_build_talker_inputs_local`` returns for a list of requests, model.py:774-805): all rows advance together, one
+        persistent-kernel launch per chunk; yields [(row, pcm_or_codes, sr, timing)] per chunk.  ``ref_codes``: None or
+        a list with one entry per row (ICL reference frames / None)."""
+        from .batching import fast_generate_streaming_batch
+        m = self.model.model
+        m.talker.rope_deltas = None
+        B = tie.shape[0]
+        st = m.speech_tokenizer if decode_audio else None
+        wins = None
+        if st is not None:
+            wins = [_StreamWindow(self, st, None if ref_codes is None else ref_codes[b], chunk_size, to_host) for b in range(B)]
+        kw = self._gen_kwargs(max_new_tokens, min_new_tokens, temperature, top_k, top_p, do_sample, repetition_penalty)
+        for items in fast_generate_streaming_batch(
+                talker=m.talker, talker_input_embeds=tie, attention_mask=tam, trailing_text_hiddens=tth,
+                tts_pad_embed=tpe, config=m.config.talker_config, chunk_size=chunk_size, uniforms=uniforms, **kw):
+            out = []
+            for b, codes, timing in items:
+                if wins is None:
+                    out.append((b, codes.cpu().numpy() if to_host else codes, self.sample_rate, timing))
+                else:
+                    audio, sr = wins[b].push(codes)
+                    out.append((b, audio, sr, timing))
+            yield out
+
+    @torch.inference_mode()
+    def generate_custom_voice_batch(self, texts: List[str], speakers: List[str], languages: List[str],
+                                    instructs: Optional[List[Optional[str]]] = None, max_new_tokens: int = 2048,
+                                    min_new_tokens: int = 2, temperature: float = 0.9, top_k: int = 50,
+                                    top_p: float = 1.0, do_sample: bool = True, repetition_penalty: float = 1.05,
+                                    non_streaming_mode: Optional[bool] = None, chunk_size: int = 8):
+        """Concurrent custom-voice requests (BASELINE config 4) sharing every pass over the weights: the prompts are
+        batched and left-padded exactly like the reference's builder does for a list of requests (model.py:583-805),
+        then decoded together.  Returns ([audio per request], sample_rate)."""
+        from .prompt import build_talker_inputs
+        self._require_type("custom_voice", "Loaded model does not support custom voice generation")
+        n = len(texts)
+        if not (len(speakers) == n and len(languages) == n):
+            raise ValueError("texts, speakers and languages must have the same length")
+        for lang, spk in zip(languages, speakers):
+            self._validate(lang, spk, check_speaker=True)
+        nsm = self._resolve_non_streaming_mode(non_streaming_mode, default=True)
+        instructs = instructs or [None] * n
+        ids = self.model._tokenize_texts([self.model._build_assistant_text(t) for t in texts])
+        ins = []
+        for i in instructs:
+            i = self._drop_instruct_for_small_model(i)
+            ins.append(None if not i else self.model._tokenize_texts([self.model._build_instruct_text(i)])[0])
+        m = self.model.model
+        tie, tam, tth, tpe = build_talker_inputs(m, input_ids=ids, ref_ids=[None] * n, voice_clone_prompt=None,
+                                                 languages=[l if l is not None else "Auto" for l in languages],
+                                                 speakers=list(speakers), non_streaming_mode=nsm, instruct_ids=ins)
+        if not self._warmed_up:
+            self.warmup(tie.shape[1])
+        parts = [[] for _ in range(n)]
+        sr = self.sample_rate
+        for items in self.stream_batch_from_embeds(tie, tam, tth, tpe, chunk_size=chunk_size,
+                                                   max_new_tokens=max_new_tokens, min_new_tokens=min_new_tokens,
+                                                   temperature=temperature, top_k=top_k, top_p=top_p,
+                                                   do_sample=do_sample, repetition_penalty=repetition_penalty):
+            for b, audio, sr, _ in items:
+                parts[b].append(audio)
+        return [np.concatenate(p) if p else np.zeros(0, dtype=np.float32) for p in parts], sr
 
     # ------------------------------------------------------------------ voice clone
     @torch.inference_mode()

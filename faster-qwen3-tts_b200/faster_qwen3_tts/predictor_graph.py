@@ -26,6 +26,7 @@ class PredictorGraph:
         self.max_seq = 2 + self.num_codebooks
         self.engine = engine
         self.captured = False
+        self.slot = 0   # request slot whose predictor cache run() uses
         self.generator: Optional[torch.Generator] = None
 
     def sampling(self) -> SamplingParams:
@@ -52,4 +53,4 @@ class PredictorGraph:
         eng = self._need_engine()
         if self.do_sample and uniforms is None:
             uniforms = torch.rand(self.num_codebooks, device=eng.device, generator=self.generator)
-        return eng.predictor_run(pred_input, self.sampling(), uniforms)
+        return eng.predictor_run(pred_input, self.sampling(), uniforms, slot=self.slot)

@@ -52,7 +52,7 @@ def fast_generate_streaming(
         t_prefill = time.time() - t0
         t1 = time.time()
         while True:
-            codes, res = engine.decode_chunk(chunk_size)
+            codes, res = engine.decode_chunk(chunk_size, slot=getattr(talker_graph, "slot", 0))
             n = res.frames_emitted
             if n:
                 total += n

@@ -32,6 +32,7 @@ class TalkerGraph:
         self.prefill_len = 0
         self.n_left_pad = 0
         self.rope_delta = 0
+        self.slot = 0   # request slot of the engine this handle drives (batch row; the reference is batch-1 here)
         self._out = None
 
     def _need_engine(self) -> Engine:
@@ -66,7 +67,7 @@ class TalkerGraph:
                 raise RuntimeError(
                     f"Input is too long: prefill has {seq_len} tokens but max_seq_len={self.max_seq_len}. "
                     "Use shorter text or shorter reference audio.")
-            eng.import_kv(li, k, v)
+            eng.import_kv(li, k, v, slot=self.slot)
         self.prefill_len = seq_len
         return seq_len
 
@@ -79,7 +80,7 @@ class TalkerGraph:
         if rope_deltas is not None:
             delta = int(round(float(rope_deltas.reshape(-1)[0].item())))
         self.n_left_pad, self.rope_delta = pad, delta
-        self._need_engine().set_generation_state(pad, delta)
+        self._need_engine().set_generation_state(pad, delta, slot=self.slot)
 
     @torch.inference_mode()
     def run(self, input_embeds: torch.Tensor, position: int) -> torch.Tensor:
@@ -87,5 +88,5 @@ class TalkerGraph:
         eng = self._need_engine()
         if self._out is None:
             self._out = torch.empty(self.hidden_size, dtype=eng.dtype, device=eng.device)
-        eng.talker_step(input_embeds, int(position), out=self._out)
+        eng.talker_step(input_embeds, int(position), out=self._out, slot=self.slot)
         return self._out.view(1, 1, -1)

@@ -99,7 +99,7 @@ def engine_tensors(talker, talker_cfg: dict, pred_cfg: dict, dtype, device, rope
 
 
 def engine_for_talker(talker, dtype=torch.bfloat16, device="cuda", max_seq_len: int = 2048, num_ctas: int = 0,
-                      native_prefill: bool = True):
+                      native_prefill: bool = True, max_batch: int = 1):
     """Build and load an fq3 Engine from the upstream talker module (``base_model.model.talker``)."""
     from .engine import Engine
 
@@ -110,7 +110,8 @@ def engine_for_talker(talker, dtype=torch.bfloat16, device="cuda", max_seq_len: 
     eng = Engine(talker=tcfg, predictor=pcfg, dtype=dtype, device=device, max_seq_len=max_seq_len,
                  num_code_groups=int(_cfg_get(tcfg_obj, "num_code_groups", 16)),
                  codec_eos_token_id=int(_cfg_get(tcfg_obj, "codec_eos_token_id")),
-                 has_mtp_projection=has_mtp_projection(talker.code_predictor), num_ctas=num_ctas)
+                 has_mtp_projection=has_mtp_projection(talker.code_predictor), num_ctas=num_ctas,
+                 max_batch=max_batch)
     tensors = engine_tensors(talker, tcfg, pcfg, dtype, eng.device, eng.rope_positions)
     eng.load_weights(tensors)
     if dtype == torch.bfloat16 and native_prefill:

@@ -61,6 +61,7 @@ typedef struct {
   int32_t rope_positions;   /* rows of the talker cos/sin tables (>= max_seq_len + margin for rope deltas) */
   fq3_stack_config talker;
   fq3_stack_config predictor;
+  int32_t max_batch;        /* request slots (KV caches + per-request state); 0/1 = one sequence, <= 32 */
 } fq3_config;
 
 /* A named tensor handed to fq3_engine_load_weights.  Names (L = layers of that stack, stacked on dim 0):
@@ -120,17 +121,28 @@ int fq3_engine_create(const fq3_config* cfg, fq3_engine** out);
 int fq3_engine_load_weights(fq3_engine* e, const fq3_tensor* tensors, int32_t n, void* stream);
 void fq3_engine_destroy(fq3_engine* e);
 
+/* Request slots.  The engine holds `max_batch` independent request slots (KV caches, predictor cache, penalty
+ * bitmap, loop state).  Every per-request entry point names its slot; fq3_decode_chunk takes the list of slots
+ * that advance together: one slot runs the single-sequence persistent kernel, several slots run the batched
+ * kernel in which all of them share ONE pass over the weight tape per step (the reference batches left-padded
+ * prompts, model.py:774-787, with per-row pad counts, talker_graph.py:177-187). */
+
 /* ---- duck-type compatibility path (what the reference's own schedulers call) ----------------------------- */
 /* TalkerGraph.prefill_kv (talker_graph.py:153-170): k,v are [n_kv, P, 128] contiguous for one layer. */
-int fq3_import_kv(fq3_engine* e, int32_t layer, const void* k_dev, const void* v_dev, int32_t P, void* stream);
-/* TalkerGraph.set_generation_state (talker_graph.py:172-196). */
-int fq3_set_generation_state(fq3_engine* e, int32_t n_left_pad, int32_t rope_delta);
+int fq3_import_kv(fq3_engine* e, int32_t slot, int32_t layer, const void* k_dev, const void* v_dev, int32_t P,
+                  void* stream);
+/* inverse of fq3_import_kv: cache rows [0,P) of one layer -> k,v [n_kv, P, 128] (what a caller holding the
+ * reference's StaticCache would read back; used by the parity tests of the hand-written prefill) */
+int fq3_export_kv(fq3_engine* e, int32_t slot, int32_t layer, void* k_dev, void* v_dev, int32_t P, void* stream);
+/* TalkerGraph.set_generation_state (talker_graph.py:172-196): per-row left-pad count and rope delta. */
+int fq3_set_generation_state(fq3_engine* e, int32_t slot, int32_t n_left_pad, int32_t rope_delta);
 /* TalkerGraph.run (talker_graph.py:198-214): one token through 28 layers + final norm.
  * embeds_dev [H] -> hidden_out_dev [H], both model dtype. */
-int fq3_talker_step(fq3_engine* e, const void* embeds_dev, int32_t position, void* hidden_out_dev, void* stream);
+int fq3_talker_step(fq3_engine* e, int32_t slot, const void* embeds_dev, int32_t position, void* hidden_out_dev,
+                    void* stream);
 /* PredictorGraph.run (predictor_graph.py:204-214): pred_input_dev [2,H_talker] -> codes_out_dev int64[15].
  * uniforms_dev float32[15] (ignored when !do_sample). */
-int fq3_predictor_run(fq3_engine* e, const void* pred_input_dev, const fq3_sampling* sp,
+int fq3_predictor_run(fq3_engine* e, int32_t slot, const void* pred_input_dev, const fq3_sampling* sp,
                       const float* uniforms_dev, int64_t* codes_out_dev, void* stream);
 /* sampling.py:32-66 + :10-29 on a single logits row (model dtype, [V]); history_dev int64[n_hist] or NULL.
  * suppress range is [V-1024,V) except eos when suppress_special != 0 (generate.py:46-50). token_out_dev int64[1]. */
@@ -143,23 +155,28 @@ int fq3_sample_logits(fq3_engine* e, const void* logits_dev, int32_t V, const fq
  * concatenated), t.o [L,H,nH*128], t.gu [L,2I,H] (gate/up rows interleaved), t.down [L,H,I], t.head [V,H]. */
 int fq3_engine_set_prefill_weights(fq3_engine* e, const fq3_tensor* tensors, int32_t n);
 /* talker.forward prefill (generate.py:107-118) + TalkerGraph.prefill_kv (talker_graph.py:153-170) in one call:
- * embeds_dev [P,H] -> KV cache slots [0,P), logits_out_dev [V] (codec_head on the last position), hidden_out_dev [H]
- * (post-norm hidden of the last position = past_hidden).  Positions are slot - n_left_pad (clamped at 0). */
-int fq3_prefill(fq3_engine* e, const void* embeds_dev, int32_t P, int32_t n_left_pad, void* logits_out_dev,
-                void* hidden_out_dev, void* stream);
+ * embeds_dev [P,H] -> KV cache slots [0,P) of request slot `slot`, logits_out_dev [V] (codec_head on the last
+ * position), hidden_out_dev [H] (post-norm hidden of the last position = past_hidden).  Positions are
+ * cache index - n_left_pad (clamped at 0); keys below n_left_pad are masked. */
+int fq3_prefill(fq3_engine* e, int32_t slot, const void* embeds_dev, int32_t P, int32_t n_left_pad,
+                void* logits_out_dev, void* hidden_out_dev, void* stream);
 
 /* ---- fused path (the persistent on-device loop) ---------------------------------------------------------- */
-/* generate.py:120-147 / streaming.py:76-104: latch per-request state.  past_hidden_dev [H] model dtype;
+/* generate.py:120-147 / streaming.py:76-104: latch per-request state of `slot`.  past_hidden_dev [H] model dtype;
  * trailing_text_dev [trailing_len,H], tts_pad_dev [H] model dtype (borrowed until the request ends);
  * uniforms_dev float32 [(max_new_tokens+1)*16]: row s+1 = draws of frame s (col 0 talker, 1..15 predictor). */
-int fq3_begin_request(fq3_engine* e, const fq3_request* rq, const void* past_hidden_dev,
+int fq3_begin_request(fq3_engine* e, int32_t slot, const fq3_request* rq, const void* past_hidden_dev,
                       const void* trailing_text_dev, const void* tts_pad_dev, const float* uniforms_dev,
                       const fq3_sampling* sp_talker, const fq3_sampling* sp_predictor, void* stream);
-/* generate.py:149-199 / streaming.py:106-173 for up to n_frames frames in ONE kernel launch.
- * codes_out_dev int64 [n_frames,16].  Synchronises the stream and fills *res. */
-int fq3_decode_chunk(fq3_engine* e, int32_t n_frames, int64_t* codes_out_dev, fq3_chunk_result* res, void* stream);
-/* last post-norm talker hidden (generate.py:198 past_hidden) -> dst_dev [H] model dtype */
-int fq3_get_past_hidden(fq3_engine* e, void* dst_dev, void* stream);
+/* generate.py:149-199 / streaming.py:106-173 for up to n_frames frames of every listed slot in ONE kernel launch.
+ * slots[n_slots] distinct slot ids that have a latched request; codes_out_dev int64 [n_slots][n_frames][16];
+ * res[n_slots] (host).  n_slots == 1: single-sequence kernel; n_slots >= 2: batched kernel, the slots advance in
+ * lock-step and stop independently (EOS / max_new_tokens / max_seq_len).  Synchronises the stream. */
+int fq3_decode_chunk(fq3_engine* e, const int32_t* slots, int32_t n_slots, int32_t n_frames, int64_t* codes_out_dev,
+                     fq3_chunk_result* res, void* stream);
+/* last post-norm talker hidden (generate.py:198 past_hidden) of `slot` -> dst_dev [H] model dtype */
+int fq3_get_past_hidden(fq3_engine* e, int32_t slot, void* dst_dev, void* stream);
+int fq3_max_batch(fq3_engine* e);
 
 /* ---- debugging / introspection ---------------------------------------------------------------------------- */
 /* When enabled, the next talker step / predictor pass 0 dumps per-layer intermediates (float32) into an engine

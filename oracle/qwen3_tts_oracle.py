@@ -186,10 +186,10 @@ def decoder_layer(
     scaling = d ** -0.5
     att = torch.matmul(q, kk.transpose(1, 2)) * scaling  # [nH, T, S]
     # causal + left-pad mask (additive, finfo.min like HF)
-    qpos = past + torch.arange(T)
-    kpos = torch.arange(S)
+    qpos = past + torch.arange(T, device=x.device)
+    kpos = torch.arange(S, device=x.device)
     allowed = (kpos[None, :] <= qpos[:, None]) & (kpos[None, :] >= n_left_pad)
-    mask = torch.zeros(T, S, dtype=att.dtype)
+    mask = torch.zeros(T, S, dtype=att.dtype, device=x.device)
     mask.masked_fill_(~allowed, torch.finfo(att.dtype).min)
     att = att + mask[None]
     att = F.softmax(att, dim=-1, dtype=torch.float32).to(q.dtype)
@@ -226,8 +226,8 @@ def run_stack(
     dbg: Optional[dict] = None,
 ) -> torch.Tensor:
     """All layers + final norm.  Returns the post-norm hidden [T,H] (what HF calls last_hidden_state)."""
-    cos = rope[0][positions].to(x.dtype)
-    sin = rope[1][positions].to(x.dtype)
+    cos = rope[0][positions].to(device=x.device, dtype=x.dtype)
+    sin = rope[1][positions].to(device=x.device, dtype=x.dtype)
     for li in range(cfg.num_hidden_layers):
         x = decoder_layer(W, prefix, cfg, li, x, cos, sin, cache, n_left_pad, dbg)
     return rms_norm(x, W[prefix + ".norm.weight"], cfg.rms_norm_eps)
@@ -366,6 +366,7 @@ def sample_token(
     suppress_tokens: Optional[List[int]] = None,
 ) -> int:
     """sampling.py:32-66 with torch.multinomial replaced by the inverse-CDF noise contract."""
+    logits = logits.detach().cpu()   # the weights (and so the logits) may live on an accelerator when tests host the oracle there
     if not do_sample:
         lg = logits.clone()
         if suppress_mask is not None:
@@ -497,6 +498,7 @@ def generate(
     n_left_pad: int = 0,
     gen_step0: int = 0,
     trace: Optional[list] = None,
+    rope_delta: Optional[int] = None,
 ):
     """generate.py:99-215 / streaming.py:57-188 restated.  Returns codes [n,16] (and chunk boundaries).
 
@@ -506,6 +508,11 @@ def generate(
     cfg = om.cfg
     eos = cfg.codec_eos_token_id
     smask = suppress_mask_for(cfg)
+    # decode positions are cache index + rope_delta on all three mRoPE axes (talker_graph.py:210-211); for a
+    # left-padded row upstream's rope_deltas is minus the pad count, so the first generated token continues the
+    # prompt's positions (arange - n_left_pad)
+    if rope_delta is None:
+        rope_delta = -n_left_pad
     if uniforms is None:
         uniforms = np.zeros((max_new_tokens + 1, 16), dtype=np.float32)
     logits, past_hidden, cache = om.talker_prefill(talker_input_embeds, n_left_pad)
@@ -533,10 +540,11 @@ def generate(
         pos = prefill_len + step_idx
         if pos >= max_seq_len - 1:
             break
-        hid = om.talker_step(x, pos, cache, n_left_pad)
-        logits = F.linear(hid, om.W["talker.codec_head.weight"])
+        hid = om.talker_step(x, pos, cache, n_left_pad, rope_delta)
+        logits = F.linear(hid, om.W["talker.codec_head.weight"]).cpu()
         if trace is not None:
-            trace.append({"x": x.float().clone(), "hidden": hid.float().clone(), "logits": logits.float().clone()})
+            trace.append({"x": x.float().cpu(), "hidden": hid.float().cpu(), "logits": logits.float().clone(),
+                          "x_raw": x.detach().clone(), "position": pos})
         if sp_talker.repetition_penalty != 1.0:
             hist = torch.tensor([r[0] for r in rows], dtype=torch.long)
             logits = apply_repetition_penalty(logits.clone(), hist, sp_talker.repetition_penalty)

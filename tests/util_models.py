@@ -23,7 +23,8 @@ def syn_cfg_from(cfg: O.ModelCfg):
 
 
 class Pair:
-    def __init__(self, cfg: O.ModelCfg, seed=0, dtype=torch.float32, max_seq_len=256, eos_boost=1.0, num_ctas=0):
+    def __init__(self, cfg: O.ModelCfg, seed=0, dtype=torch.float32, max_seq_len=256, eos_boost=1.0, num_ctas=0,
+                 max_batch=1, oracle_device="cpu"):
         from faster_qwen3_tts import synthetic
         from faster_qwen3_tts.predictor_graph import PredictorGraph
         from faster_qwen3_tts.talker_graph import TalkerGraph
@@ -31,12 +32,14 @@ class Pair:
         self.cfg = cfg
         self.dtype = dtype
         self.W = O.make_weights(cfg, seed=seed, dtype=dtype, eos_boost=eos_boost)
-        self.om = O.OracleModel(cfg, self.W)
+        # the oracle is plain torch: full-size cases host it on the accelerator (torch eager = the reference's own
+        # arithmetic on this GPU) so that they finish in seconds
+        self.om = O.OracleModel(cfg, self.W if oracle_device == "cpu" else {k: v.to(oracle_device) for k, v in self.W.items()})
         self.syn = syn_cfg_from(cfg)
         self.base = synthetic.build_base_model(self.syn, self.W, dtype=dtype, device="cuda")
         self.talker = self.base.model.talker
         self.engine = engine_for_talker(self.talker, dtype=dtype, device="cuda", max_seq_len=max_seq_len,
-                                        num_ctas=num_ctas)
+                                        num_ctas=num_ctas, max_batch=max_batch)
         self.pg = PredictorGraph(self.talker.code_predictor, self.syn.code_predictor_config, cfg.talker.hidden_size,
                                  dtype=dtype, engine=self.engine)
         self.tg = TalkerGraph(self.talker.model, self.syn.talker_config, dtype=dtype, max_seq_len=max_seq_len,
