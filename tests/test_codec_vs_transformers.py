@@ -83,3 +83,10 @@ def test_code2wav_matches_hf_analogue(T, monkeypatch):
     err = (got.reshape(-1) - want.reshape(-1)).abs().max().item()
     print(f"T={T}: max abs PCM diff {err:.2e} (|pcm| max {want.abs().max():.3f})")
     assert want.abs().max() > 0.05 and err < 5e-6   # O(1) activations at every stage: float rounding only
+    # the functional fp32 ORACLE (oracle/codec_oracle.py, the checker of the 1e-3 PCM bar) on the same weights
+    from oracle import codec_oracle
+    with torch.inference_mode():
+        ora = codec_oracle.decode(mine.state_dict(), codes[0].transpose(0, 1), codebook_size=64, num_attention_heads=4)
+    err_o = (ora - want.reshape(-1)).abs().max().item()
+    print(f"T={T}: oracle vs HF analogue max abs PCM diff {err_o:.2e}")
+    assert ora.shape[0] == 1920 * T and err_o < 5e-6

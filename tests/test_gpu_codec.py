@@ -1,0 +1,79 @@
+"""PCM bar of BASELINE.json's north_star: "output audio matches the reference on fixed seeds within 1e-3 max-abs PCM".
+
+The engine's codec path (`speech_tokenizer.decode`, C ABI `fq3_codec_decode` for the waveform stack) against the fp32
+ORACLE decode held under oracle/ (oracle/codec_oracle.py, pinned to the Hugging Face Code2Wav analogue on CPU), same
+weights, same codes, at the FULL decoder geometry (1536 -> 96 channels, rates 8*5*4*3) and at the two window lengths the
+streaming policy produces (model.py:1085-1135): Phase 2 = 25 context + 8 new frames (T=33), Phase 1 with an ICL
+reference = 174 + 8 frames (T=182).  Tolerance 1e-3 max-abs, as north_star states."""
+import pytest
+import torch
+
+from oracle import codec_oracle
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-3
+
+
+@pytest.fixture(scope="module")
+def full_codec():
+    from faster_qwen3_tts.codec import Code2WavConfig, build_codec
+    cfg = Code2WavConfig()
+    assert cfg.decoder_dim == 1536 and tuple(cfg.upsample_rates) == (8, 5, 4, 3)
+    return build_codec(cfg, seed=3, dtype=torch.bfloat16, device="cuda", backend="engine")
+
+
+def _oracle(st, codes):
+    c = st.decoder.config
+    with torch.inference_mode():
+        return codec_oracle.decode(st.decoder.state_dict(), codes, codebook_size=c.codebook_size,
+                                   num_attention_heads=c.num_attention_heads, sliding_window=c.sliding_window,
+                                   rms_norm_eps=c.rms_norm_eps, rope_theta=c.rope_theta,
+                                   upsampling_ratios=c.upsampling_ratios, upsample_rates=c.upsample_rates)
+
+
+@pytest.mark.parametrize("T", [33, 182, 8])
+def test_full_geometry_window_pcm_within_1e3_of_fp32_oracle(full_codec, T):
+    st = full_codec
+    codes = torch.randint(0, 2048, (T, 16), generator=torch.Generator().manual_seed(T), device="cpu").cuda()
+    got, sr = st.decode({"audio_codes": codes[None]})
+    want = _oracle(st, codes)
+    assert sr == 24000 and got[0].shape[0] == 1920 * T == want.shape[0]
+    err = (got[0] - want).abs().max().item()
+    peak, rms = want.abs().max().item(), want.pow(2).mean().sqrt().item()
+    print(f"T={T}: max|engine - fp32 oracle| = {err:.3e}  (oracle peak {peak:.3f}, rms {rms:.4f})")
+    assert peak > 0.02            # a real signal reaches the output
+    assert err < TOL
+
+
+def test_streaming_windows_end_to_end_codes_to_pcm(full_codec):
+    """codes -> PCM through the reference's window policy (ICL reference of 174 frames, chunk 8): every emitted chunk
+    against the oracle decoding the same window with the same trim."""
+    from faster_qwen3_tts.model import _StreamWindow
+    import types
+    st = full_codec
+    g = torch.Generator().manual_seed(5)
+    ref = torch.randint(0, 2048, (174, 16), generator=g).cuda()
+    owner = types.SimpleNamespace(_to_numpy=None)
+    win = _StreamWindow(owner, st, ref, 8, to_host=False)
+    gen = []
+    worst = 0.0
+    for ci in range(6):
+        chunk = torch.randint(0, 2048, (8, 16), generator=g).cuda()
+        gen.append(chunk)
+        audio, sr = win.push(chunk)
+        flat = torch.cat(gen)
+        n_total = flat.shape[0]
+        if ci < 4:      # Phase 1 (fewer than 25 generated frames before this chunk completes calibration at 32)
+            inp = torch.cat([ref, flat])
+            full = _oracle(st, inp)
+            cut = int(174 / inp.shape[0] * full.shape[0])
+            want = full[cut:][(n_total - 8) * 1920:]
+        else:           # Phase 2: 25 context frames + the 8 new ones
+            window = flat[n_total - 8 - 25:]
+            want = _oracle(st, window)[25 * 1920:]
+        assert audio.shape[0] == want.shape[0] == 8 * 1920, (ci, audio.shape, want.shape)
+        err = (audio - want).abs().max().item()
+        worst = max(worst, err)
+        print(f"chunk {ci}: max|d| = {err:.3e}")
+    assert worst < TOL

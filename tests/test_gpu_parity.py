@@ -252,10 +252,12 @@ def test_full_size_bf16_step_logits_and_structure():
     assert int(codes[:, 0].max()) < 2048 and int(codes[:, 1:].max()) < 2048
 
 
-def test_codec_stack_kernels_vs_torch_module():
-    """K4: the hand-written conv/ConvTranspose/SnakeBeta stack (C ABI) against the same weights in the torch module.
-    fp32 torch is the reference; the bf16 torch (cuDNN) path is the yardstick for what bf16 arithmetic costs."""
+def test_codec_stack_kernels_vs_fp32_oracle_reduced_geometry():
+    """K4 at a reduced geometry (fast): engine decode against the fp32 oracle decode (oracle/codec_oracle.py) at the
+    north_star's PCM bar, plus causality of the window (a prefix decodes to the same samples).  The full-geometry gate
+    lives in tests/test_gpu_codec.py."""
     from faster_qwen3_tts.codec import Code2WavConfig, build_codec
+    from oracle import codec_oracle
     cfg = Code2WavConfig(hidden_size=256, num_hidden_layers=2, num_attention_heads=4, intermediate_size=512,
                          decoder_dim=512, codebook_size=64)
     st = build_codec(cfg, seed=3, dtype=torch.bfloat16, device="cuda", backend="engine")
@@ -263,15 +265,11 @@ def test_codec_stack_kernels_vs_torch_module():
     got, sr = st.decode({"audio_codes": codes})
     assert sr == 24000 and got[0].shape[0] == 9 * 1920
     with torch.inference_mode():
-        import copy
-        ref32 = copy.deepcopy(st.decoder).float()(codes.transpose(1, 2))[0, 0]
-        ref16 = st.decoder(codes.transpose(1, 2))[0, 0].float()
+        ref32 = codec_oracle.decode(st.decoder.state_dict(), codes[0], codebook_size=64, num_attention_heads=4,
+                                    sliding_window=cfg.sliding_window, rms_norm_eps=cfg.rms_norm_eps)
     e_engine = (got[0] - ref32).abs().max().item()
-    e_torch16 = (ref16 - ref32).abs().max().item()
-    print(f"codec max|engine - fp32| = {e_engine:.4e}   max|torch bf16 - fp32| = {e_torch16:.4e}  "
-          f"rms ref {ref32.pow(2).mean().sqrt().item():.3e}")
-    assert e_engine < max(3 * e_torch16, 2e-2)
-    # causality / windowing: decoding a prefix gives the same samples
+    print(f"codec max|engine - fp32 oracle| = {e_engine:.4e}  peak {ref32.abs().max().item():.3f} rms {ref32.pow(2).mean().sqrt().item():.3e}")
+    assert e_engine < 1e-3
     got2, _ = st.decode({"audio_codes": codes[:, :5]})
     assert (got2[0] - got[0][: 5 * 1920]).abs().max().item() < 1e-6
 
