@@ -213,6 +213,7 @@ struct __align__(128) Smem {
   volatile int prod_done;   // producer -> consumers
   volatile int prod_issued; // tiles issued by the producer
   int bst[5][32];           // batched kernel: replicated per-column loop state (token, step, gen_step, finished, emitted)
+  long long prof[12];       // batched kernel, CTA 0 / thread 0: [0] last clock [1] current category [2..] cycles per category
 };
 
 // All dynamic shared memory of the kernel is one Smem; going through this accessor (instead of a reference carried

@@ -41,6 +41,24 @@ struct SlotParams {
 
 enum { BS_TOK = 0, BS_STEP = 1, BS_GEN = 2, BS_FIN = 3, BS_EMIT = 4 };
 
+// phase accounting (dbg_on & 2): CTA 0 / thread 0 charges the clock64 cycles since the last mark to the category that
+// was current; dumped to the debug buffer at the end of the launch (tools/batch_bench.py --phases)
+enum { PC_OTHER = 0, PC_GEMV = 1, PC_BARRIER = 2, PC_NORM = 3, PC_ATTN = 4, PC_SAMPLE = 5, PC_N = 6 };
+__device__ __forceinline__ void pmark(Ctx& c, int cat) {
+  if ((c.P.dbg_on & 2) && blockIdx.x == 0 && c.tid == 0) {
+    Smem& s = SMEM();
+    const long long now = clock64();
+    s.prof[2 + (int)s.prof[1]] += now - s.prof[0];
+    s.prof[0] = now;
+    s.prof[1] = cat;
+  }
+}
+__device__ __forceinline__ void grid_sync_p(Ctx& c, int next_cat) {
+  pmark(c, PC_BARRIER);
+  grid_sync(c);
+  pmark(c, next_cat);
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // GEMV epilogues (what the single-sequence kernel expresses as lambdas)
 // ------------------------------------------------------------------------------------------------------------
@@ -759,13 +777,13 @@ __device__ void stack_b(Ctx& c, const StackDev& S, const BView& v, int nt, uint3
                          reinterpret_cast<uint8_t*>(P.XNB) + (size_t)col * P.ldX * (BF ? 2 : 4), nullptr, nullptr, v.rank, nparts);
         }
     }
-    grid_sync(c);
+    grid_sync_p(c, PC_GEMV);
     // ---- QKV rows
     {
       EpiB e{EP_F32, P.QKVB, nullptr, P.ldQKV, nullptr, 0, nullptr};
       gemv_b<BF>(c, S.seg_base + 4 * l + 0, S.H, P.XNB, P.ldX, ncols, e);
     }
-    grid_sync(c);
+    grid_sync_p(c, PC_ATTN);
     // ---- attention
     if constexpr (TALKER) {
       int idx = 0;
@@ -787,13 +805,13 @@ __device__ void stack_b(Ctx& c, const StackDev& S, const BView& v, int nt, uint3
         else attn_small_b<BF, 2>(c, S, l, 0, 0, q0, (size_t)B * P.ldQKV, me.pkc, me.pvc, a0, (size_t)B * P.ldATT);
       }
     }
-    grid_sync(c);
+    grid_sync_p(c, PC_GEMV);
     // ---- o_proj + residual
     {
       EpiB e{EP_RESID, P.X1B, nullptr, P.ldX, P.XB, P.ldX, nullptr};
       gemv_b<BF>(c, S.seg_base + 4 * l + 1, S.qd, P.ATTB, P.ldATT, ncols, e);
     }
-    grid_sync(c);
+    grid_sync_p(c, PC_NORM);
     // ---- post-attention norm
     if (mine && v.rank < nparts)
       for (int t = 0; t < nt; ++t) {
@@ -802,19 +820,19 @@ __device__ void stack_b(Ctx& c, const StackDev& S, const BView& v, int nt, uint3
         norm_row_b<BF>(c, [&](int k) { return __ldcg(src + k); }, S.ln_post, (size_t)l * S.H, S.H, S.eps,
                        reinterpret_cast<uint8_t*>(P.XNB) + (size_t)col * P.ldX * (BF ? 2 : 4), nullptr, nullptr, v.rank, nparts);
       }
-    grid_sync(c);
+    grid_sync_p(c, PC_GEMV);
     // ---- gate/up + SiLU*up
     {
       EpiB e{EP_SWIGLU, nullptr, P.ACTB, P.ldACT, nullptr, 0, nullptr};
       gemv_b<BF>(c, S.seg_base + 4 * l + 2, S.H, P.XNB, P.ldX, ncols, e);
     }
-    grid_sync(c);
+    grid_sync_p(c, PC_GEMV);
     // ---- down + residual
     {
       EpiB e{EP_RESID, P.XB, nullptr, P.ldX, P.X1B, P.ldX, nullptr};
       gemv_b<BF>(c, S.seg_base + 4 * l + 3, S.I, P.ACTB, P.ldACT, ncols, e);
     }
-    grid_sync(c);
+    grid_sync_p(c, PC_NORM);
   }
   // final norm of the last token -> XNB row b (head GEMV input); talker: also the slot's past_hidden
   if (mine && v.rank < nparts) {
@@ -824,7 +842,7 @@ __device__ void stack_b(Ctx& c, const StackDev& S, const BView& v, int nt, uint3
                    reinterpret_cast<uint8_t*>(P.XNB) + (size_t)v.b * P.ldX * (BF ? 2 : 4), nullptr,
                    TALKER ? me.past_hidden : nullptr, v.rank, nparts);
   }
-  grid_sync(c);
+  grid_sync_p(c, PC_GEMV);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -910,6 +928,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) fq3_decode_batch_kernel(const __g
     const int Ht = P.t.H;
     const size_t esz = BF ? 2 : 4;
     const StackDev& Sp = P.p;
+    if (tid == 0) {
+      for (int i = 0; i < 12; ++i) s.prof[i] = 0;
+      s.prof[0] = clock64();
+    }
     const int npp = min(v.gsz, Sp.H / NCT);   // CTAs sharing the writes of a predictor norm row
     const int npt = min(v.gsz, Ht / NCT);     // ... of a talker norm row
     while (true) {
@@ -947,14 +969,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) fq3_decode_batch_kernel(const __g
               stw<BF>(dst, k, t == 0 ? __ldcg(me.past_hidden + k) : ldw<BF>(P.t_embed, (size_t)token * Ht + k));
           }
         }
-        grid_sync(c);
+        grid_sync_p(c, PC_GEMV);
         EpiB e{EP_BIAS, P.XB, nullptr, P.ldX, nullptr, 0, P.mtp_b};
         gemv_b<BF>(c, P.seg_mtp, Ht, P.PINB, HMAX, 2 * B, e);
-        grid_sync(c);
+        grid_sync_p(c, PC_NORM);
       }
       for (int i = 0; i < P.ncb; ++i) {
         const int nt = (i == 0) ? 2 : 1;
         // ---- layer-0 input norm of this pass (raw rows -> XB, normalised rows -> XNB)
+        pmark(c, PC_NORM);
         if (mine && v.rank < npp) {
           for (int t = 0; t < nt; ++t) {
             const int col = t * B + v.b;
@@ -979,7 +1002,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fq3_decode_batch_kernel(const __g
           EpiB e{EP_F32, P.LOGB, nullptr, VMAX, nullptr, 0, nullptr};
           gemv_b<BF>(c, Sp.seg_head + i, Sp.H, P.XNB, P.ldX, B, e);
         }
-        grid_sync(c);
+        grid_sync_p(c, PC_SAMPLE);
         if (mine) {
           SampleArgs sa;
           sa.logits = P.LOGB + (size_t)v.b * VMAX; sa.V = Sp.V; sa.sp = me.sp_p;
@@ -990,6 +1013,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fq3_decode_batch_kernel(const __g
           csync();
         }
       }
+      pmark(c, PC_OTHER);
       // ---- emit the frame (generate.py:159): cat(cb0, 15 ids)
       if (mine && v.rank == 0 && tid < 16) me.codes_out[(size_t)s.bst[BS_EMIT][v.b] * 16 + tid] = (long long)s.codes[tid];
       csync();
@@ -1016,6 +1040,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fq3_decode_batch_kernel(const __g
       const bool mine2 = (run2 >> v.b) & 1u;
       // ================= talker step =================
       // layer-0 input: sum of 16 embedding rows + trailing text / tts_pad (generate.py:163-171)
+      pmark(c, PC_NORM);
       if (mine2 && v.rank < npt) {
         const void* extra = gen_step < me.trailing_len ? me.trailing : me.tts_pad;
         const size_t eoff = gen_step < me.trailing_len ? (size_t)gen_step * Ht : 0;
@@ -1032,7 +1057,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fq3_decode_batch_kernel(const __g
         EpiB e{EP_F32, P.LOGB, nullptr, VMAX, nullptr, 0, nullptr};
         gemv_b<BF>(c, P.t.seg_head, Ht, P.XNB, P.ldX, B, e);
       }
-      grid_sync(c);
+      grid_sync_p(c, PC_SAMPLE);
       if (mine2) {
         SampleArgs sa;
         sa.logits = P.LOGB + (size_t)v.b * VMAX; sa.V = P.t.V; sa.sp = me.sp_t;
@@ -1042,7 +1067,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fq3_decode_batch_kernel(const __g
         const int tok = sample_block<BF>(c, sa);
         if (v.rank == 0 && tid == 0) P.TOKB[v.b] = tok;
       }
-      grid_sync(c);
+      grid_sync_p(c, PC_OTHER);
       if (tid < B && ((run2 >> tid) & 1u)) {
         s.bst[BS_TOK][tid] = __ldcg(P.TOKB + tid);
         s.bst[BS_STEP][tid] += 1;
@@ -1050,6 +1075,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) fq3_decode_batch_kernel(const __g
       }
       csync();
     }
+    pmark(c, PC_OTHER);
+    if ((P.dbg_on & 2) && cta == 0 && tid == 0)
+      for (int i = 0; i < PC_N; ++i) reinterpret_cast<long long*>(P.dbg)[i] = s.prof[2 + i];
     if (v.rank == 0) {
       if (tid == 0) {
         int* st = me.state;

@@ -962,7 +962,7 @@ static int launch_decode_batch(fq3_engine* e, const int32_t* slots, int n, int n
   kp.nslots = n;
   kp.sl = e->sl_dev;
   kp.n_frames = n_frames;
-  kp.dbg_on = 0;
+  kp.dbg_on = e->dbg_on & 2;
   void* args[] = {(void*)&kp};
   if (e->bf16)
     CK(cudaLaunchCooperativeKernel((const void*)fq3_decode_batch_kernel<true>, dim3(e->ncta), dim3(NTHREADS), args, smem_bytes(), stream));

@@ -435,7 +435,7 @@ class OracleModel:
                         self.W.get("talker.code_predictor.small_to_mtp_projection.bias"))
 
     def predictor_frame(self, past_hidden: torch.Tensor, last_id_hidden: torch.Tensor, sp: SamplingParams,
-                        uniforms: Optional[np.ndarray] = None, dbg=None) -> List[int]:
+                        uniforms: Optional[np.ndarray] = None, dbg=None, margins: Optional[list] = None) -> List[int]:
         """predictor_graph.py:115-167 -- 2-token prefill, then 14 single-token decodes; 15 ids."""
         pc = self.cfg.predictor
         nb = self.cfg.num_code_groups - 1
@@ -446,6 +446,9 @@ class OracleModel:
         logits = F.linear(hid[-1], self.W["talker.code_predictor.lm_head.0.weight"])
         if dbg is not None:
             dbg["pred.logits0"] = logits.float()
+        if margins is not None:   # top-1 minus top-2 logit of every pass (how close a greedy decision is to a tie)
+            t2 = torch.topk(logits.float(), 2).values
+            margins.append(float(t2[0] - t2[1]))
         tok = sample_token(logits, temperature=sp.temperature, top_k=sp.top_k, top_p=sp.top_p,
                            do_sample=sp.do_sample, u=float(uniforms[0]) if uniforms is not None else 0.0)
         out.append(tok)
@@ -454,6 +457,9 @@ class OracleModel:
             h = self._mtp(emb[None])
             hid = run_stack(self.W, "talker.code_predictor.model", pc, h, torch.tensor([1 + i]), cache, self.rope_p)
             logits = F.linear(hid[-1], self.W[f"talker.code_predictor.lm_head.{i}.weight"])
+            if margins is not None:
+                t2 = torch.topk(logits.float(), 2).values
+                margins.append(float(t2[0] - t2[1]))
             tok = sample_token(logits, temperature=sp.temperature, top_k=sp.top_k, top_p=sp.top_p,
                                do_sample=sp.do_sample, u=float(uniforms[i]) if uniforms is not None else 0.0)
             out.append(tok)
@@ -529,7 +535,8 @@ def generate(
         if token == eos:
             break
         last_id_hidden = om.codec_embed(token)
-        codes15 = om.predictor_frame(past_hidden, last_id_hidden, sp_pred, uniforms[step_idx + 1, 1:16])
+        pm = [] if trace is not None else None
+        codes15 = om.predictor_frame(past_hidden, last_id_hidden, sp_pred, uniforms[step_idx + 1, 1:16], margins=pm)
         rows.append([token] + codes15)
         buf += 1
         if gen_step < trailing_text_hiddens.shape[0]:
@@ -544,7 +551,7 @@ def generate(
         logits = F.linear(hid, om.W["talker.codec_head.weight"]).cpu()
         if trace is not None:
             trace.append({"x": x.float().cpu(), "hidden": hid.float().cpu(), "logits": logits.float().clone(),
-                          "x_raw": x.detach().clone(), "position": pos})
+                          "x_raw": x.detach().clone(), "position": pos, "pred_margins": pm})
         if sp_talker.repetition_penalty != 1.0:
             hist = torch.tensor([r[0] for r in rows], dtype=torch.long)
             logits = apply_repetition_penalty(logits.clone(), hist, sp_talker.repetition_penalty)

@@ -41,9 +41,15 @@ def test_full_geometry_window_pcm_within_1e3_of_fp32_oracle(full_codec, T):
     assert sr == 24000 and got[0].shape[0] == 1920 * T == want.shape[0]
     err = (got[0] - want).abs().max().item()
     peak, rms = want.abs().max().item(), want.pow(2).mean().sqrt().item()
-    print(f"T={T}: max|engine - fp32 oracle| = {err:.3e}  (oracle peak {peak:.3f}, rms {rms:.4f})")
+    # yardstick: the same bf16 weights through the torch / cuDNN modules (the arithmetic the reference itself executes)
+    with torch.inference_mode():
+        lib16 = st.decoder(codes.t()[None])[0, 0].float()
+    err_lib = (lib16 - want).abs().max().item()
+    print(f"T={T}: max|engine - fp32 oracle| = {err:.3e}  max|torch bf16 modules - fp32 oracle| = {err_lib:.3e}  "
+          f"(oracle peak {peak:.3f}, rms {rms:.4f})")
     assert peak > 0.02            # a real signal reaches the output
     assert err < TOL
+    assert err < 1.5 * err_lib + 1e-5   # bf16 arithmetic costs the hand-written path no more than the library path
 
 
 def test_streaming_windows_end_to_end_codes_to_pcm(full_codec):
