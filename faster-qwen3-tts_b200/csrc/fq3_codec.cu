@@ -49,6 +49,8 @@ __global__ void conv_out_kernel(const __nv_bfloat16* __restrict__ X, const float
                                 int C, int taps, float* __restrict__ out) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= T) return;
+  X += (size_t)blockIdx.y * T * C;      // blockIdx.y = sequence of the batch
+  out += (size_t)blockIdx.y * T;
   float s = bias;
   for (int k = 0; k < taps; ++k) {
     const int tt = t - (taps - 1 - k);
@@ -68,6 +70,8 @@ __global__ void conv_out_kernel(const __nv_bfloat16* __restrict__ X, const float
 // (output of the upsampling front end) arrives channels-first from torch -> transpose + cast here
 __global__ void to_channels_last_kernel(const __nv_bfloat16* __restrict__ X, int C, int T, __nv_bfloat16* __restrict__ Y) {
   __shared__ __nv_bfloat16 tile[32][33];
+  X += (size_t)blockIdx.z * C * T;      // blockIdx.z = sequence of the batch
+  Y += (size_t)blockIdx.z * C * T;
   const int c0 = blockIdx.y * 32, t0 = blockIdx.x * 32;
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
     const int c = c0 + i, t = t0 + threadIdx.x;
@@ -267,26 +271,29 @@ extern "C" int fq3_codec_load_weights(fq3_codec* c, const fq3_tensor* tensors, i
 }
 
 static int launch_conv(fq3_codec* c, const Layer& L, const __nv_bfloat16* X, const __nv_bfloat16* R, __nv_bfloat16* Yraw,
-                       __nv_bfloat16* Yact, int T, cudaStream_t stream) {
+                       __nv_bfloat16* Yact, int T, int batch, cudaStream_t stream) {
   ConvArgs a;
   a.X = X; a.W = L.W; a.bias = L.bias; a.R = R; a.Yraw = Yraw; a.Yact = Yact; a.ea = L.ea; a.ib = L.ib;
   a.T = T; a.Cin = L.Cin; a.N = L.N; a.taps = L.taps; a.dil = L.dil; a.bias_mod = L.bias_mod; a.act_mod = L.act_mod;
   a.mode = 0;
+  a.batch = batch;
   c->launches++;
   if (g_fq3_gemm_backend == 0) {
     const int r = fq3tc::launch_tc(a, stream);
     if (r == 0) return 0;
     if (r < 0) return cfail(FQ3_ERR_CUDA, "tcgen05 conv launch failed: ", cudaGetErrorString(cudaGetLastError()));
   }
-  dim3 grid((T + BM - 1) / BM, (L.N + BN - 1) / BN);
+  dim3 grid(((T + BM - 1) / BM) * batch, (L.N + BN - 1) / BN);
   conv_gemm_kernel<<<grid, CTHREADS, CONV_SMEM, stream>>>(a);
   CCK(cudaGetLastError());
   return 0;
 }
 
-// x_dev: [hidden][T4] bf16 channels-first (output of the torch front end), pcm_out_dev float32 [T4 * prod(rates)]
-extern "C" int fq3_codec_decode(fq3_codec* c, const void* x_dev, int32_t T4, float* pcm_out_dev, void* stream_) {
-  if (!c || !x_dev || !pcm_out_dev || T4 <= 0) return cfail(FQ3_ERR_INVALID, "null argument");
+// x_dev: [batch][hidden][T4] bf16 channels-first (output of the front end), pcm_out_dev float32 [batch][T4 * prod(rates)]:
+// `batch` independent windows of equal length share every launch (each with its own causal left padding)
+extern "C" int fq3_codec_decode_batch(fq3_codec* c, const void* x_dev, int32_t batch, int32_t T4, float* pcm_out_dev,
+                                      void* stream_) {
+  if (!c || !x_dev || !pcm_out_dev || T4 <= 0 || batch <= 0) return cfail(FQ3_ERR_INVALID, "null argument");
   if (c->layers.empty()) return cfail(FQ3_ERR_STATE, "codec weights not loaded");
   CCK(cudaSetDevice(c->dev));
   cudaStream_t stream = (cudaStream_t)stream_;
@@ -302,13 +309,14 @@ extern "C" int fq3_codec_decode(fq3_codec* c, const void* x_dev, int32_t T4, flo
       need = std::max(need, T * (size_t)C);
     }
   }
+  need *= (size_t)batch;
   if (need > c->cap) {
     for (auto*& b : c->buf) { if (b) cudaFree(b); b = nullptr; }
     for (auto*& b : c->buf) CCK(cudaMalloc(&b, need * 2));
     c->cap = need;
   }
   {
-    dim3 g((T4 + 31) / 32, (c->hidden + 31) / 32), b(32, 8);
+    dim3 g((T4 + 31) / 32, (c->hidden + 31) / 32, batch), b(32, 8);
     to_channels_last_kernel<<<g, b, 0, stream>>>((const __nv_bfloat16*)x_dev, c->hidden, T4, c->buf[0]);
     c->launches++;
   }
@@ -317,7 +325,7 @@ extern "C" int fq3_codec_decode(fq3_codec* c, const void* x_dev, int32_t T4, flo
   size_t li = 0;
   // four ping-pong buffers.  `cur` always holds the activated input of the next layer; the other three are free.
   __nv_bfloat16* cur = c->buf[1];
-  if ((rc = launch_conv(c, c->layers[li++], c->buf[0], nullptr, nullptr, cur, T, stream))) return rc;
+  if ((rc = launch_conv(c, c->layers[li++], c->buf[0], nullptr, nullptr, cur, T, batch, stream))) return rc;
   for (int bi = 0; bi < c->n_blocks; ++bi) {
     __nv_bfloat16* f[3];
     int k = 0;
@@ -325,23 +333,27 @@ extern "C" int fq3_codec_decode(fq3_codec* c, const void* x_dev, int32_t T4, flo
       if (b != cur) f[k++] = b;
     __nv_bfloat16 *x = f[0], *a1 = f[1], *a2 = f[2], *y = cur;  // cur is free once the up-conv has consumed it
     const Layer& U = c->layers[li++];
-    if ((rc = launch_conv(c, U, cur, nullptr, x, a1, T, stream))) return rc;  // raw -> x, SnakeBeta(raw) -> a1
+    if ((rc = launch_conv(c, U, cur, nullptr, x, a1, T, batch, stream))) return rc;  // raw -> x, SnakeBeta(raw) -> a1
     T *= U.upsample;
     for (int j = 0; j < 3; ++j) {
       const Layer& C1 = c->layers[li++];
       const Layer& C2 = c->layers[li++];
-      if ((rc = launch_conv(c, C1, a1, nullptr, nullptr, a2, T, stream))) return rc;  // a2 = act2(conv7(a1))
+      if ((rc = launch_conv(c, C1, a1, nullptr, nullptr, a2, T, batch, stream))) return rc;  // a2 = act2(conv7(a1))
       // y = conv1(a2) + x ; a1 <- SnakeBeta_next(y)   (conv7 has consumed a1, so it can be overwritten)
-      if ((rc = launch_conv(c, C2, a2, x, C2.write_raw ? y : nullptr, a1, T, stream))) return rc;
+      if ((rc = launch_conv(c, C2, a2, x, C2.write_raw ? y : nullptr, a1, T, batch, stream))) return rc;
       std::swap(x, y);
     }
     cur = a1;
   }
   __nv_bfloat16* act = cur;
-  conv_out_kernel<<<(T + 255) / 256, 256, 0, stream>>>(act, c->w_out, c->b_out, T, c->c_out, 7, pcm_out_dev);
+  conv_out_kernel<<<dim3((T + 255) / 256, batch), 256, 0, stream>>>(act, c->w_out, c->b_out, T, c->c_out, 7, pcm_out_dev);
   c->launches++;
   CCK(cudaGetLastError());
   return 0;
+}
+
+extern "C" int fq3_codec_decode(fq3_codec* c, const void* x_dev, int32_t T4, float* pcm_out_dev, void* stream_) {
+  return fq3_codec_decode_batch(c, x_dev, 1, T4, pcm_out_dev, stream_);
 }
 
 extern "C" double fq3_codec_flops(fq3_codec* c, int32_t T4) { return c ? c->flops_per_frame * T4 : 0.0; }

@@ -41,7 +41,7 @@ constexpr int MAXGRP = 512;          // row groups per CTA
 constexpr int MAXSEG = 256;          // GEMV segments
 constexpr int SEQMAX = 4096;
 
-enum Mode { MODE_FUSED = 0, MODE_TALKER_STEP = 1, MODE_PRED_RUN = 2, MODE_BARRIER_TEST = 3 };
+enum Mode { MODE_FUSED = 0, MODE_TALKER_STEP = 1, MODE_PRED_RUN = 2, MODE_BARRIER_TEST = 3, MODE_GEMV_TEST = 4 };
 
 struct Grp {           // one row group of one segment, as seen by one CTA (<= 32 rows, full K)
   uint32_t off16;      // tape offset / 16
@@ -116,6 +116,11 @@ struct KParams {
   float *XB, *X1B, *QKVB, *LOGB;   // fp32 [MAXCOL][ldX] / [MAXCOL][ldX] / [MAXCOL][ldQKV] / [MAXB][VMAX]
   void *XNB, *ATTB, *ACTB, *PINB;  // model dtype GEMV inputs [MAXCOL][ldX] / [ldATT] / [ldACT] / [HMAX]
   int* TOKB;                   // [MAXB] cb0 token of every column after the talker sampling step
+  int batch_exact;             // 1: batched bf16 GEMVs keep the single-sequence kernel's summation order (bit-identical rows)
+  // MODE_GEMV_TEST: one batched GEMV over segment `gt_seg` (numerics test of the GEMV against a torch reference)
+  int gt_seg, gt_K, gt_ncols, gt_rows, gt_swiglu;
+  const void* gt_x;            // model dtype [gt_ncols][gt_K]
+  void* gt_out;                // fp32 [gt_ncols][gt_rows]  (gt_swiglu: model dtype [gt_ncols][gt_rows / 2])
 };
 
 // ------------------------------------------------------------------------------------------------------------
@@ -214,6 +219,7 @@ struct __align__(128) Smem {
   volatile int prod_issued; // tiles issued by the producer
   int bst[5][32];           // batched kernel: replicated per-column loop state (token, step, gen_step, finished, emitted)
   long long prof[12];       // batched kernel, CTA 0 / thread 0: [0] last clock [1] current category [2..] cycles per category
+  int runl[36];             // batched kernel: columns running in the current (sub)frame, ascending; [32] = their number
 };
 
 // All dynamic shared memory of the kernel is one Smem; going through this accessor (instead of a reference carried

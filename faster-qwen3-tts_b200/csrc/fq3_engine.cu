@@ -362,6 +362,8 @@ extern "C" int fq3_engine_create(const fq3_config* cfg, fq3_engine** out) {
   k.XB = e->XB; k.X1B = e->X1B; k.QKVB = e->QKVB; k.LOGB = e->LOGB;
   k.XNB = e->XNB; k.ATTB = e->ATTB; k.ACTB = e->ACTB; k.PINB = e->PINB; k.TOKB = e->TOKB;
   k.nslots = 0; k.sl = e->sl_dev;
+  k.batch_exact = 0;
+  if (const char* v = getenv("FQ3_BATCH_EXACT")) k.batch_exact = atoi(v) ? 1 : 0;   // bit-identical to the single-sequence kernel
   k.has_mtp = cfg->has_mtp_projection; k.ncb = cfg->num_code_groups - 1; k.eos = cfg->codec_eos_token_id;
   k.max_seq_len = cfg->max_seq_len;
   k.dbg = e->dbg; k.dbg_stride_layer = e->dbg_stride;
@@ -969,6 +971,50 @@ static int launch_decode_batch(fq3_engine* e, const int32_t* slots, int n, int n
   else
     CK(cudaLaunchCooperativeKernel((const void*)fq3_decode_batch_kernel<false>, dim3(e->ncta), dim3(NTHREADS), args, smem_bytes(), stream));
   e->launches++;
+  return 0;
+}
+
+// numerics probe: ONE batched GEMV (the kernel the batched decode path is built from) over a weight segment
+extern "C" int fq3_debug_gemv(fq3_engine* e, int32_t stack, int32_t layer, int32_t which, int32_t ncols, const void* x_dev,
+                              void* out_dev, void* stream_) {
+  if (!e || !x_dev || !out_dev) return fail(FQ3_ERR_INVALID, "null argument");
+  if (!e->loaded) return fail(FQ3_ERR_STATE, "weights not loaded");
+  if (!e->sl_dev) return fail(FQ3_ERR_STATE, "engine was created with max_batch = 1");
+  if (ncols < 1 || ncols > MAXCOL) return fail(FQ3_ERR_INVALID, "ncols out of range");
+  const StackDev& S = stack == 0 ? e->kp.t : e->kp.p;
+  int sg;
+  if (which >= 0 && which < 4) {
+    if (layer < 0 || layer >= S.L) return fail(FQ3_ERR_INVALID, "layer out of range");
+    sg = S.seg_base + 4 * layer + which;
+  } else if (which == 4) {
+    sg = S.seg_head + (stack == 0 ? 0 : layer);
+  } else {
+    return fail(FQ3_ERR_INVALID, "which must be 0..4 (qkv, o, gate/up, down, head)");
+  }
+  DevGuard dev_guard(e->dev);
+  cudaStream_t stream = (cudaStream_t)stream_;
+  CK(cudaMemsetAsync(e->bar, 0, 32768, stream));
+  KParams kp = e->kp;
+  kp.mode = MODE_GEMV_TEST;
+  kp.nslots = 1;
+  kp.sl = e->sl_dev;
+  kp.n_frames = 0;
+  kp.dbg_on = 0;
+  kp.gt_seg = sg; kp.gt_K = e->segs[sg].K; kp.gt_rows = e->segs[sg].rows; kp.gt_ncols = ncols;
+  kp.gt_swiglu = which == 2 ? 1 : 0;
+  kp.gt_x = x_dev; kp.gt_out = out_dev;
+  void* args[] = {(void*)&kp};
+  if (e->bf16)
+    CK(cudaLaunchCooperativeKernel((const void*)fq3_decode_batch_kernel<true>, dim3(e->ncta), dim3(NTHREADS), args, smem_bytes(), stream));
+  else
+    CK(cudaLaunchCooperativeKernel((const void*)fq3_decode_batch_kernel<false>, dim3(e->ncta), dim3(NTHREADS), args, smem_bytes(), stream));
+  e->launches++;
+  return 0;
+}
+
+extern "C" int fq3_set_batch_exact(fq3_engine* e, int32_t on) {
+  if (!e) return fail(FQ3_ERR_INVALID, "null argument");
+  e->kp.batch_exact = on ? 1 : 0;
   return 0;
 }
 

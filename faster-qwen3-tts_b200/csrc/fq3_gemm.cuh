@@ -26,6 +26,8 @@ struct ConvArgs {
   const float* ib;          // 1 / (exp(beta) + 1e-9) [act_mod]
   int T, Cin, N, taps, dil, bias_mod, act_mod;
   int mode;                 // 0 general, 1 SwiGLU pair epilogue (Yraw is [T][N/2])
+  int batch;                // independent sequences: X is [batch][T][Cin], R / Yraw / Yact are [batch][T][N]; every
+                            // sequence has its own causal left padding (0 or 1 = a single sequence)
 };
 
 __device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -59,9 +61,13 @@ static __global__ void __launch_bounds__(CTHREADS, 2) conv_gemm_kernel(  // stat
   uint8_t* sB = smem + STAGES * A_BYTES;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int wm = warp >> 2, wn = warp & 3;  // 2 x 4 warps; warp tile 64 x 24
-  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  const int tiles_m = (a.T + BM - 1) / BM;
+  const int bidx = blockIdx.x / tiles_m;     // sequence of the batch
+  const int m0 = (blockIdx.x - bidx * tiles_m) * BM, n0 = blockIdx.y * BN;
   const int kc = a.Cin / BK;                 // k-steps per tap
   const int nks = a.taps * kc;
+  const __nv_bfloat16* Xb = a.X + (size_t)bidx * a.T * a.Cin;
+  const size_t ybase = (size_t)bidx * a.T * a.N;
 
   auto load_stage = [&](int ks, int stage) {
     const int tap = ks / kc, c0 = (ks - tap * kc) * BK;
@@ -74,7 +80,7 @@ static __global__ void __launch_bounds__(CTHREADS, 2) conv_gemm_kernel(  // stat
       const int row = q >> 2, ch = q & 3;
       const int t = m0 + row - shift;
       const bool ok = t >= 0 && t < a.T && (m0 + row) < a.T;
-      const __nv_bfloat16* src = a.X + ((size_t)(ok ? t : 0) * a.Cin + c0 + ch * 8);
+      const __nv_bfloat16* src = Xb + ((size_t)(ok ? t : 0) * a.Cin + c0 + ch * 8);
       cp_async16(A + swz(row, ch), src, ok);
     }
 #pragma unroll
@@ -156,14 +162,14 @@ static __global__ void __launch_bounds__(CTHREADS, 2) conv_gemm_kernel(  // stat
         if (a.mode == 1) {
           const float gte = __bfloat162float(__float2bfloat16_rn(v0)), up = __bfloat162float(__float2bfloat16_rn(v1));
           const float sl = __bfloat162float(__float2bfloat16_rn(gte / (1.0f + expf(-gte))));
-          a.Yraw[(size_t)m * (a.N >> 1) + (n >> 1)] = __float2bfloat16_rn(sl * up);
+          a.Yraw[(ybase >> 1) + (size_t)m * (a.N >> 1) + (n >> 1)] = __float2bfloat16_rn(sl * up);
           continue;
         }
         if (a.bias) {
           v0 += a.bias[n % a.bias_mod];
           v1 += a.bias[(n + 1) % a.bias_mod];
         }
-        const size_t off = (size_t)m * a.N + n;
+        const size_t off = ybase + (size_t)m * a.N + n;
         if (a.R) {  // torch: conv/linear output is a bf16 tensor, THEN the residual add (second rounding)
           const __nv_bfloat162 r = *reinterpret_cast<const __nv_bfloat162*>(a.R + off);
           v0 = __bfloat162float(__float2bfloat16_rn(v0)) + __bfloat162float(r.x);

@@ -57,6 +57,10 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, in
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                ::"r"(su32(dst)), "l"(tm), "r"(su32(bar)), "r"(c0), "r"(c1) : "memory");
 }
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tm, int c0, int c1, int c2, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+               ::"r"(su32(dst)), "l"(tm), "r"(su32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
 __device__ __forceinline__ uint64_t smem_desc(const void* p, uint32_t sbo, uint64_t layout) {
   uint64_t d = 0;
   d |= (uint64_t)((su32(p) >> 4) & 0x3fff);   // start address
@@ -99,7 +103,9 @@ static __global__ void __launch_bounds__(TTHREADS, DEEP ? 1 : 2)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum + 1);
   float* ep = reinterpret_cast<float*>(tiles + C::STAGES * C::STAGE + 256);  // [3][TBN]: bias, exp(alpha), 1/(exp(beta)+eps)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * TBM, n0 = blockIdx.y * TBN;
+  const int tiles_m = (a.T + TBM - 1) / TBM;
+  const int bidx = blockIdx.x / tiles_m;   // sequence of the batch (own causal padding: TMA zero-fills rows < 0 of ITS time axis)
+  const int m0 = (blockIdx.x - bidx * tiles_m) * TBM, n0 = blockIdx.y * TBN;
   const int kc = a.Cin / BK, nks = a.taps * kc;
 
   if (threadIdx.x == 0) {
@@ -129,7 +135,7 @@ static __global__ void __launch_bounds__(TTHREADS, DEEP ? 1 : 2)
         uint8_t* A = tiles + s * C::STAGE;
         uint8_t* B = A + C::A_BYTES;
         mb_expect(&full[s], C::STAGE);
-        tma_load_2d(A, &tmX, c0, m0 - shift, &full[s]);          // rows < 0 or >= T are zero-filled by TMA
+        tma_load_3d(A, &tmX, c0, m0 - shift, bidx, &full[s]);    // rows < 0 or >= T of this sequence are zero-filled by TMA
         tma_load_2d(B, &tmW, tap * a.Cin + c0, n0, &full[s]);
       }
     }
@@ -172,7 +178,7 @@ static __global__ void __launch_bounds__(TTHREADS, DEEP ? 1 : 2)
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
     if (m < a.T) {
       if (a.mode == 1) {
-        __nv_bfloat16* dst = a.Yraw + (size_t)m * (a.N >> 1) + (n0 >> 1);
+        __nv_bfloat16* dst = a.Yraw + ((size_t)bidx * a.T + m) * (a.N >> 1) + (n0 >> 1);
 #pragma unroll
         for (int j = 0; j < 3; ++j) {
           __align__(16) __nv_bfloat16 o[16];
@@ -189,7 +195,7 @@ static __global__ void __launch_bounds__(TTHREADS, DEEP ? 1 : 2)
           }
         }
       } else {
-        const size_t off = (size_t)m * a.N + n0;
+        const size_t off = ((size_t)bidx * a.T + m) * a.N + n0;
 #pragma unroll
         for (int j = 0; j < 3; ++j) {
 #pragma unroll
@@ -262,6 +268,20 @@ static bool make_map(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t 
             CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// 3-D bf16 [batch][rows][cols] with box [1][box_rows][box_cols]: out-of-range rows of ONE sequence read as zero
+static bool make_map3(CUtensorMap* tm, const void* base, uint64_t batch, uint64_t rows, uint64_t cols, uint32_t box_rows,
+                      uint32_t box_cols) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return false;
+  const cuuint64_t dims[3] = {cols, rows, batch};
+  const cuuint64_t strides[2] = {cols * 2, rows * cols * 2};
+  const cuuint32_t box[3] = {box_cols, box_rows, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  const CUtensorMapSwizzle sw = box_cols == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  return fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 // returns 0 on success, 1 if this shape must use the mma.sync fallback, <0 on CUDA error
 static int launch_tc(const fq3gemm::ConvArgs& a, cudaStream_t stream) {
   static bool attr_done = false;
@@ -281,9 +301,10 @@ static int launch_tc(const fq3gemm::ConvArgs& a, cudaStream_t stream) {
   if ((a.Yraw && ((uintptr_t)a.Yraw & 15)) || (a.Yact && ((uintptr_t)a.Yact & 15)) || (a.R && ((uintptr_t)a.R & 15))) return 1;
   if (a.mode == 1 ? (a.N % 32 != 0) : (a.N % 8 != 0)) return 1;
   CUtensorMap tmX, tmW;
-  if (!make_map(&tmX, a.X, (uint64_t)a.T, (uint64_t)a.Cin, TBM, BK)) return 1;
+  const int nb = a.batch > 1 ? a.batch : 1;
+  if (!make_map3(&tmX, a.X, (uint64_t)nb, (uint64_t)a.T, (uint64_t)a.Cin, TBM, BK)) return 1;
   if (!make_map(&tmW, a.W, (uint64_t)a.N, (uint64_t)a.taps * a.Cin, TBN, BK)) return 1;
-  dim3 grid((a.T + TBM - 1) / TBM, (a.N + TBN - 1) / TBN);
+  dim3 grid(((a.T + TBM - 1) / TBM) * nb, (a.N + TBN - 1) / TBN);
   const bool deep = (long long)grid.x * grid.y <= (long long)num_sms * 3 / 2;
   if (BK == 64) {
     if (deep) conv_gemm_tc_kernel<64, 1><<<grid, TTHREADS, Cfg<64, 1>::SMEM, stream>>>(tmX, tmW, a);

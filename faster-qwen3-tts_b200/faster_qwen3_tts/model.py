@@ -38,18 +38,28 @@ class _StreamWindow:
         self.all_codes, self.prev_len, self.spf = [], 0, None
         self.conv = owner._to_numpy if to_host else (lambda a: a.flatten())
 
-    def push(self, codec_chunk):
+    def window(self, codec_chunk):
+        """-> (codes [T,16] to decode, meta): the decode call the policy makes for this chunk"""
         self.all_codes.append(codec_chunk)
         n_new = codec_chunk.shape[0]
         flat = torch.cat(self.all_codes, dim=0)
         n_total = flat.shape[0]
-        ref_codes = self.ref_codes
         if self.spf is None:
+            ref_codes = self.ref_codes
             inp = torch.cat([ref_codes.to(flat.device), flat], dim=0) if ref_codes is not None else flat
-            audio_list, sr = self.st.decode({"audio_codes": inp.unsqueeze(0)})
-            audio = self.conv(audio_list[0])
-            if ref_codes is not None:
-                cut = int(ref_codes.shape[0] / max(inp.shape[0], 1) * len(audio))
+            return inp, ("phase1", n_total, int(inp.shape[0]))
+        start = max(0, n_total - n_new - CONTEXT_FRAMES)
+        window = flat[start:]
+        return window, ("phase2", window.shape[0] - n_new, 0)
+
+    def finish(self, audio, meta):
+        """decoded window -> the new samples of this chunk (trim of the reference / of the 25-frame context)"""
+        audio = self.conv(audio)
+        kind, a, b = meta
+        if kind == "phase1":
+            n_total, n_inp = a, b
+            if self.ref_codes is not None:
+                cut = int(self.ref_codes.shape[0] / max(n_inp, 1) * len(audio))
                 gen_audio = audio[cut:]
             else:
                 gen_audio = audio
@@ -57,14 +67,30 @@ class _StreamWindow:
             self.prev_len = len(gen_audio)
             if n_total >= self.min_cal:
                 self.spf = len(gen_audio) / n_total
-        else:
-            start = max(0, n_total - n_new - CONTEXT_FRAMES)
-            window = flat[start:]
-            n_ctx = window.shape[0] - n_new
-            audio_list, sr = self.st.decode({"audio_codes": window.unsqueeze(0)})
-            audio = self.conv(audio_list[0])
-            new_audio = audio[int(round(n_ctx * self.spf)):] if n_ctx > 0 else audio
-        return new_audio, sr
+            return new_audio
+        n_ctx = a
+        return audio[int(round(n_ctx * self.spf)):] if n_ctx > 0 else audio
+
+    def push(self, codec_chunk):
+        codes, meta = self.window(codec_chunk)
+        audio_list, sr = self.st.decode({"audio_codes": codes.unsqueeze(0)})
+        return self.finish(audio_list[0], meta), sr
+
+
+def decode_windows_batched(speech_tokenizer, wins, chunks):
+    """One chunk of several requests: windows of equal length are decoded as ONE batch (every codec launch covers all of
+    them); returns [(new_audio, sample_rate)] in the order of `wins`."""
+    prepared = [w.window(c) for w, c in zip(wins, chunks)]
+    groups = {}
+    for i, (codes, _) in enumerate(prepared):
+        groups.setdefault(int(codes.shape[0]), []).append(i)
+    out = [None] * len(wins)
+    sr = speech_tokenizer.sample_rate if hasattr(speech_tokenizer, "sample_rate") else 24000
+    for T, idxs in groups.items():
+        audio_list, sr = speech_tokenizer.decode({"audio_codes": torch.stack([prepared[i][0] for i in idxs])})
+        for i, a in zip(idxs, audio_list):
+            out[i] = (wins[i].finish(a, prepared[i][1]), sr)
+    return out
 
 
 class FasterQwen3TTS:
@@ -447,14 +473,11 @@ class FasterQwen3TTS:
         for items in fast_generate_streaming_batch(
                 talker=m.talker, talker_input_embeds=tie, attention_mask=tam, trailing_text_hiddens=tth,
                 tts_pad_embed=tpe, config=m.config.talker_config, chunk_size=chunk_size, uniforms=uniforms, **kw):
-            out = []
-            for b, codes, timing in items:
-                if wins is None:
-                    out.append((b, codes.cpu().numpy() if to_host else codes, self.sample_rate, timing))
-                else:
-                    audio, sr = wins[b].push(codes)
-                    out.append((b, audio, sr, timing))
-            yield out
+            if wins is None:
+                yield [(b, codes.cpu().numpy() if to_host else codes, self.sample_rate, timing) for b, codes, timing in items]
+                continue
+            dec = decode_windows_batched(st, [wins[b] for b, _, _ in items], [codes for _, codes, _ in items])
+            yield [(b, audio, sr, timing) for (b, _, timing), (audio, sr) in zip(items, dec)]
 
     @torch.inference_mode()
     def generate_custom_voice_batch(self, texts: List[str], speakers: List[str], languages: List[str],

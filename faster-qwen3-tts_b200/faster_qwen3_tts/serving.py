@@ -81,8 +81,10 @@ class ContinuousBatcher:
     ``BatchScheduler`` of batching.py); ``window_factory(ref_codes)`` -> object with ``push(codes) -> (pcm, sr)``
     (``model._StreamWindow``)."""
 
-    def __init__(self, scheduler, window_factory: Callable, chunk_size: int = 8, idle_sleep: float = 0.002):
+    def __init__(self, scheduler, window_factory: Callable, chunk_size: int = 8, idle_sleep: float = 0.002,
+                 batch_decode: Optional[Callable] = None):
         self.sched, self.window_factory, self.chunk_size = scheduler, window_factory, chunk_size
+        self.batch_decode = batch_decode   # (windows, code chunks) -> [(pcm, sr)]: one codec batch per window length
         self.idle_sleep = idle_sleep
         self.pending: "queue.Queue[Ticket]" = queue.Queue()
         self.live: Dict[int, tuple] = {}     # rid -> (ticket, window)
@@ -137,11 +139,18 @@ class ContinuousBatcher:
                 self.live.clear()
                 continue
             self.steps += 1
+            live = [(rq, codes) for rq, codes in results if int(codes.shape[0])]
+            # windows of equal length of all requests are decoded as one batch when the window objects support it
+            pcm_of = {}
+            if live and self.batch_decode is not None:
+                for (rq, _), (pcm, sr) in zip(live, self.batch_decode([self.live[rq.tag][1] for rq, _ in live],
+                                                                      [codes for _, codes in live])):
+                    pcm_of[rq.tag] = (pcm, sr)
             for rq, codes in results:
                 t, win = self.live[rq.tag]
                 n = int(codes.shape[0])
                 if n:
-                    pcm, sr = win.push(codes)
+                    pcm, sr = pcm_of[rq.tag] if rq.tag in pcm_of else win.push(codes)
                     if t.first_chunk_at is None:
                         t.first_chunk_at = time.time()
                     t.frames += n
@@ -155,7 +164,7 @@ class ContinuousBatcher:
 def batcher_for_model(model, chunk_size: int = 8, to_host: bool = True) -> ContinuousBatcher:
     """ContinuousBatcher over a ``FasterQwen3TTS`` whose engine was created with ``max_batch`` > 1."""
     from .batching import BatchScheduler
-    from .model import _StreamWindow
+    from .model import _StreamWindow, decode_windows_batched
     m = model.model.model
     sched = BatchScheduler(model.engine, m.talker, m.config.talker_config, model.predictor_graph, model.talker_graph)
     st = m.speech_tokenizer
@@ -167,7 +176,8 @@ def batcher_for_model(model, chunk_size: int = 8, to_host: bool = True) -> Conti
     def window(ref_codes):
         return _StreamWindow(model, st, ref_codes, chunk_size, to_host) if st is not None else _CodesOnly()
 
-    return ContinuousBatcher(sched, window, chunk_size=chunk_size)
+    bd = (lambda wins, chunks: decode_windows_batched(st, wins, chunks)) if st is not None else None
+    return ContinuousBatcher(sched, window, chunk_size=chunk_size, batch_decode=bd)
 
 
 def voice_clone_request(model, text: str, language: str, ref_audio, ref_text: str = "", xvec_only: bool = False,

@@ -177,6 +177,14 @@ int fq3_decode_chunk(fq3_engine* e, const int32_t* slots, int32_t n_slots, int32
 /* last post-norm talker hidden (generate.py:198 past_hidden) of `slot` -> dst_dev [H] model dtype */
 int fq3_get_past_hidden(fq3_engine* e, int32_t slot, void* dst_dev, void* stream);
 int fq3_max_batch(fq3_engine* e);
+/* batched bf16 GEMVs: 0 (default) = fast summation order, 1 = the single-sequence kernel's order (every row of a batched
+ * launch then reproduces a single-slot launch bit for bit; also settable with FQ3_BATCH_EXACT=1 at engine creation) */
+int fq3_set_batch_exact(fq3_engine* e, int32_t on);
+/* numerics probe of the batched GEMV: y[col][row] = W_seg[row,:] . x[col,:] for one weight segment of stack 0 (talker) /
+ * 1 (predictor): which 0 qkv, 1 o_proj, 2 gate/up (out = model dtype [ncols][I] = silu(gate)*up), 3 down, 4 head
+ * (predictor: layer = codebook).  x_dev model dtype [ncols][K]; out_dev float32 [ncols][rows] (which != 2). */
+int fq3_debug_gemv(fq3_engine* e, int32_t stack, int32_t layer, int32_t which, int32_t ncols, const void* x_dev,
+                   void* out_dev, void* stream);
 
 /* ---- debugging / introspection ---------------------------------------------------------------------------- */
 /* When enabled, the next talker step / predictor pass 0 dumps per-layer intermediates (float32) into an engine
@@ -199,6 +207,9 @@ typedef struct fq3_codec fq3_codec;
 int fq3_codec_create(const int32_t* geom, int32_t n_geom, fq3_codec** out);
 int fq3_codec_load_weights(fq3_codec* c, const fq3_tensor* tensors, int32_t n, void* stream);
 int fq3_codec_decode(fq3_codec* c, const void* x_dev, int32_t T4, float* pcm_out_dev, void* stream);
+/* `batch` windows of equal length in one set of launches (concurrent requests, BASELINE config 4): x_dev bf16
+ * [batch][hidden][T4], pcm float32 [batch][T4*prod(rates)]; every window has its own causal left padding. */
+int fq3_codec_decode_batch(fq3_codec* c, const void* x_dev, int32_t batch, int32_t T4, float* pcm_out_dev, void* stream);
 double fq3_codec_flops(fq3_codec* c, int32_t T4);
 int64_t fq3_codec_launch_count(fq3_codec* c);
 void fq3_codec_destroy(fq3_codec* c);

@@ -21,6 +21,7 @@ ap.add_argument("--frames", type=int, default=32)
 ap.add_argument("--chunk", type=int, default=8)
 ap.add_argument("--batches", default="1,2,4,8,16,32")
 ap.add_argument("--fp32", action="store_true")
+ap.add_argument("--modes", default="fast", help="comma list of fast,exact (batched bf16 GEMV summation order), measured back to back")
 ap.add_argument("--phases", action="store_true", help="clock64 phase accounting of CTA 0 over the last launch")
 a = ap.parse_args()
 Bs = [int(x) for x in a.batches.split(",")]
@@ -29,7 +30,9 @@ cfg = synthetic.make_config(a.size)
 model = FasterQwen3TTS.from_synthetic(a.size, dtype=dt, with_codec=False, max_seq_len=2048, max_batch=max(Bs))
 eng = model.engine
 m = model.model.model
-for B in Bs:
+for B, mode in [(B, md) for B in Bs for md in a.modes.split(",")]:
+    eng.set_batch_exact(mode == "exact")
+
     def run():
         sched = BatchScheduler(eng, m.talker, m.config.talker_config, model.predictor_graph, model.talker_graph)
         for b in range(B):
@@ -48,13 +51,14 @@ for B in Bs:
     run()
     if a.phases:
         eng.debug_enable(2)
+        c0 = eng.probe_timestamps(6).tolist()
     n, ms = run()
     ph = None
     if a.phases:
-        cyc = eng.probe_timestamps(6).tolist()
+        cyc = [b - x for b, x in zip(eng.probe_timestamps(6).tolist(), c0)]
         eng.debug_enable(0)
         names = ["other", "gemv", "barrier", "norm", "attn", "sample"]
-        ph = {k: round(v / 1.965e3 / a.chunk, 1) for k, v in zip(names, cyc)}   # us per frame-step at 1965 MHz (last launch)
+        ph = {k: round(v / 1.965e3 / (n / B), 1) for k, v in zip(names, cyc)}   # us per frame-step at 1965 MHz (CTA 0)
     steps = n / B
-    print(json.dumps({"B": B, "size": a.size, "dtype": str(dt), "frames": n, "ms": round(ms, 3), "ms_per_frame_step": round(ms / steps, 4),
+    print(json.dumps({"B": B, "mode": mode, "size": a.size, "dtype": str(dt), "frames": n, "ms": round(ms, 3), "ms_per_frame_step": round(ms / steps, 4),
                       "agg_frames_per_s": round(n / ms * 1000, 1), "agg_rtf": round(n * 0.08 / (ms / 1000), 1), "phase_us_per_frame": ph}), flush=True)
