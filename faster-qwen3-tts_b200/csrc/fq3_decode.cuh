@@ -116,7 +116,6 @@ struct KParams {
   float *XB, *X1B, *QKVB, *LOGB;   // fp32 [MAXCOL][ldX] / [MAXCOL][ldX] / [MAXCOL][ldQKV] / [MAXB][VMAX]
   void *XNB, *ATTB, *ACTB, *PINB;  // model dtype GEMV inputs [MAXCOL][ldX] / [ldATT] / [ldACT] / [HMAX]
   int* TOKB;                   // [MAXB] cb0 token of every column after the talker sampling step
-  int batch_exact;             // 1: batched bf16 GEMVs keep the single-sequence kernel's summation order (bit-identical rows)
   // MODE_GEMV_TEST: one batched GEMV over segment `gt_seg` (numerics test of the GEMV against a torch reference)
   int gt_seg, gt_K, gt_ncols, gt_rows, gt_swiglu;
   const void* gt_x;            // model dtype [gt_ncols][gt_K]

@@ -233,161 +233,6 @@ __device__ __noinline__ void gemv_mma_b(Ctx& c, int seg, int K, const __nv_bfloa
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// FAST bf16 tensor-core GEMV over up to 32 activation columns (default; gemv_mma_b above is the bit-exact-with-the-
-// single-sequence-kernel variant kept behind FQ3_BATCH_EXACT=1).
-//   * a warp owns one (m-tile, n-group) combination -- HALF tiles: one group of 4 tokens -- and sweeps the k-groups of
-//     every ring tile itself: 4 accumulator registers, no cross-warp partial sums when there are >= 5 combinations;
-//     with fewer combinations the k-groups are dealt round-robin to KS warps per combination and the KS partials are
-//     added in a fixed order (deterministic);
-//   * the B fragments (activations, straight from L2) run through a D-deep software pipeline that is independent of the
-//     tile boundaries: the loads of the next D k-groups are in flight while the current one feeds the tensor cores and
-//     while the warp waits for the next weight tile.
-// ------------------------------------------------------------------------------------------------------------
-__device__ __noinline__ void gemv_mma_c(Ctx& c, int seg, int K, const __nv_bfloat16* __restrict__ xg, int ldx, int col0,
-                                        int ncols, const EpiB e) {
-  float* red = SMEM().xs;  // [KS][combo][4][32]
-  const uint32_t st = SMEM().seg[seg];
-  const int gbeg = (int)(st >> 8), gn = (int)(st & 255u);
-  const int gq = c.lane >> 2, t = c.lane & 3;
-  const int ngr = (ncols + 7) >> 3, ngh = (ncols + 3) >> 2;
-  for (int gi = 0; gi < gn; ++gi) {
-    const Grp g = SMEM().grp[gbeg + gi];
-    const int n_mt = g.rows & 0xff, kind = g.rows >> 8, G = g.m, ntiles = g.ntiles;
-    const int ncombo = kind == 1 ? ngh : n_mt * ngr;
-    const int KS = ncombo >= 5 ? 1 : (ncombo >= 3 ? 2 : (ncombo == 2 ? 4 : 8));
-    const int combo = c.warp % ncombo, ks = c.warp / ncombo;
-    const bool active = ks < KS;
-    const int mt = kind == 1 ? 0 : combo / ngr, ng = kind == 1 ? combo : combo % ngr;
-    // this lane's B-operand row (column of the activation matrix) and, for the warp that applies the epilogue, the
-    // values the epilogue needs from global memory (fetched now, used after the sweep)
-    const __nv_bfloat16* xb;
-    if (kind != 1) {
-      const int col = ng * 8 + gq;
-      xb = xg + (size_t)(col0 + (col < ncols ? col : 0)) * ldx + 16 * t;
-    } else {
-      const int tok = ng * 4 + (gq >> 1);
-      xb = xg + (size_t)(col0 + (tok < ncols ? tok : 0)) * ldx + (gq & 1) * (K >> 1) + 16 * t;
-    }
-    float aux[4] = {0.f, 0.f, 0.f, 0.f};
-    if (active && ks == 0) {
-      if (kind == 0) {
-        const int rA = g.row0 + mt * 16 + gq, cA = ng * 8 + 2 * t;
-        if (cA < ncols) { aux[0] = epi_pre<true>(e, rA, col0 + cA); aux[2] = epi_pre<true>(e, rA + 8, col0 + cA); }
-        if (cA + 1 < ncols) { aux[1] = epi_pre<true>(e, rA, col0 + cA + 1); aux[3] = epi_pre<true>(e, rA + 8, col0 + cA + 1); }
-      } else if (kind == 1) {
-        const int tok = ng * 4 + t;
-        if (tok < ncols) aux[0] = epi_pre<true>(e, g.row0 + gq, col0 + tok);
-      }
-    }
-    const int kgt = ntiles * G;                                   // k-groups of this row group
-    const int nj = active ? (kgt - ks + KS - 1) / KS : 0;         // ... of which this warp takes ks, ks+KS, ...
-    constexpr int D = 4;
-    uint4 blo[D], bhi[D];
-#pragma unroll
-    for (int d = 0; d < D; ++d) {
-      if (d < nj) {
-        blo[d] = __ldcg(reinterpret_cast<const uint4*>(xb + 64 * (ks + d * KS)));
-        bhi[d] = __ldcg(reinterpret_cast<const uint4*>(xb + 64 * (ks + d * KS) + 8));
-      } else {
-        blo[d] = make_uint4(0, 0, 0, 0);
-        bhi[d] = make_uint4(0, 0, 0, 0);
-      }
-    }
-    // 2 x D independent accumulator sets: consecutive k-groups (and the two halves of one k-group) never wait for each
-    // other's tensor-core latency; they are added in a fixed order at the end
-    float acc[D][2][4];
-#pragma unroll
-    for (int d = 0; d < D; ++d)
-#pragma unroll
-      for (int h2 = 0; h2 < 2; ++h2)
-#pragma unroll
-        for (int r = 0; r < 4; ++r) acc[d][h2][r] = 0.f;
-    int cur = -1;        // ring tile currently held by this warp (-1: none yet)
-    int need = 0, qq = ks;   // tile / k-group-in-tile of the next k-group of this warp
-    while (qq >= G) { qq -= G; ++need; }
-    auto advance_to = [&](int tile) {
-      while (cur < tile) {
-        if (cur >= 0) {
-          __syncwarp();
-          if (c.lane == 0) mbar_arrive(&SMEM().empty[(int)((c.tile_ctr + (uint32_t)cur) % NS)]);
-        }
-        ++cur;
-        const uint32_t tc = c.tile_ctr + (uint32_t)cur;
-        mbar_wait(&SMEM().full[(int)(tc % NS)], (tc / NS) & 1u);
-      }
-    };
-    int j = 0;
-    while (j < nj) {
-#pragma unroll
-      for (int d = 0; d < D; ++d) {
-        if (j < nj) {
-          advance_to(need);
-          const uint8_t* tile = SMEM().ring[(int)((c.tile_ctr + (uint32_t)cur) % NS)];
-          const uint4* A = reinterpret_cast<const uint4*>(tile + ((size_t)(mt * G + qq) * 4) * 512) + c.lane;
-          const uint4 a0 = A[0], a1 = A[32], a2 = A[64], a3 = A[96];
-          mma_bf16(acc[d][0], a0, blo[d].x, blo[d].y);
-          mma_bf16(acc[d][1], a1, blo[d].z, blo[d].w);
-          mma_bf16(acc[d][0], a2, bhi[d].x, bhi[d].y);
-          mma_bf16(acc[d][1], a3, bhi[d].z, bhi[d].w);
-          if (j + D < nj) {
-            const int kgn = ks + (j + D) * KS;
-            blo[d] = __ldcg(reinterpret_cast<const uint4*>(xb + 64 * kgn));
-            bhi[d] = __ldcg(reinterpret_cast<const uint4*>(xb + 64 * kgn + 8));
-          }
-          ++j;
-          qq += KS;
-          while (qq >= G) { qq -= G; ++need; }
-        }
-      }
-    }
-    advance_to(ntiles - 1);   // walk (and hand back) every tile, also those this warp had no k-group in
-    __syncwarp();
-    if (c.lane == 0) mbar_arrive(&SMEM().empty[(int)((c.tile_ctr + (uint32_t)cur) % NS)]);
-    c.tile_ctr += (uint32_t)ntiles;
-    float cv[4];
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      float sm = 0.f;
-#pragma unroll
-      for (int d = 0; d < D; ++d) sm += acc[d][0][r] + acc[d][1][r];
-      cv[r] = sm;
-    }
-    if (KS > 1) {
-      if (active)
-#pragma unroll
-        for (int r = 0; r < 4; ++r) red[((ks * ncombo + combo) * 4 + r) * 32 + c.lane] = cv[r];
-      csync();
-      if (active && ks == 0) {
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-          float sm = 0.f;
-          for (int k2 = 0; k2 < KS; ++k2) sm += red[((k2 * ncombo + combo) * 4 + r) * 32 + c.lane];
-          cv[r] = sm;
-        }
-      }
-    }
-    if (active && ks == 0) {
-      if (kind == 1) {
-        const int tok = ng * 4 + t;
-        if (tok < ncols) epi_apply<true>(e, g.row0 + gq, col0 + tok, cv[0] + cv[3], 0.f, aux[0]);
-      } else {
-        const int cA = ng * 8 + 2 * t;
-        if (kind == 2) {
-          const int pair = g.row0 + mt * 8 + gq;
-          if (cA < ncols) epi_apply<true>(e, pair, col0 + cA, cv[0], cv[2], 0.f);
-          if (cA + 1 < ncols) epi_apply<true>(e, pair, col0 + cA + 1, cv[1], cv[3], 0.f);
-        } else {
-          const int rA = g.row0 + mt * 16 + gq;
-          if (cA < ncols) { epi_apply<true>(e, rA, col0 + cA, cv[0], 0.f, aux[0]); epi_apply<true>(e, rA + 8, col0 + cA, cv[2], 0.f, aux[2]); }
-          if (cA + 1 < ncols) { epi_apply<true>(e, rA, col0 + cA + 1, cv[1], 0.f, aux[1]); epi_apply<true>(e, rA + 8, col0 + cA + 1, cv[3], 0.f, aux[3]); }
-        }
-      }
-    }
-    if (KS > 1) csync();   // red is reused by the next group
-  }
-}
-
-// ------------------------------------------------------------------------------------------------------------
 // fp32 (parity mode) GEMV over up to 8 activation columns: gemv_seg<false, NT> with x read from global memory.
 // ------------------------------------------------------------------------------------------------------------
 __device__ __noinline__ void gemv_seg_b(Ctx& c, int seg, const float* __restrict__ xg, int ldx, int col0, int ncols,
@@ -485,8 +330,7 @@ __device__ __forceinline__ void gemv_b(Ctx& c, int seg, int K, const void* xg, i
     const __nv_bfloat16* x = reinterpret_cast<const __nv_bfloat16*>(xg);
     for (int c0 = 0; c0 < ncols; c0 += 32) {
       const int n = min(32, ncols - c0);
-      if (!c.P.batch_exact) gemv_mma_c(c, seg, K, x, ldx, c0, n, e);
-      else if (n <= 8) gemv_mma_b<1>(c, seg, K, x, ldx, c0, n, e);
+      if (n <= 8) gemv_mma_b<1>(c, seg, K, x, ldx, c0, n, e);
       else if (n <= 16) gemv_mma_b<2>(c, seg, K, x, ldx, c0, n, e);
       else gemv_mma_b<4>(c, seg, K, x, ldx, c0, n, e);
     }

@@ -362,8 +362,6 @@ extern "C" int fq3_engine_create(const fq3_config* cfg, fq3_engine** out) {
   k.XB = e->XB; k.X1B = e->X1B; k.QKVB = e->QKVB; k.LOGB = e->LOGB;
   k.XNB = e->XNB; k.ATTB = e->ATTB; k.ACTB = e->ACTB; k.PINB = e->PINB; k.TOKB = e->TOKB;
   k.nslots = 0; k.sl = e->sl_dev;
-  k.batch_exact = 0;
-  if (const char* v = getenv("FQ3_BATCH_EXACT")) k.batch_exact = atoi(v) ? 1 : 0;   // bit-identical to the single-sequence kernel
   k.has_mtp = cfg->has_mtp_projection; k.ncb = cfg->num_code_groups - 1; k.eos = cfg->codec_eos_token_id;
   k.max_seq_len = cfg->max_seq_len;
   k.dbg = e->dbg; k.dbg_stride_layer = e->dbg_stride;
@@ -1009,12 +1007,6 @@ extern "C" int fq3_debug_gemv(fq3_engine* e, int32_t stack, int32_t layer, int32
   else
     CK(cudaLaunchCooperativeKernel((const void*)fq3_decode_batch_kernel<false>, dim3(e->ncta), dim3(NTHREADS), args, smem_bytes(), stream));
   e->launches++;
-  return 0;
-}
-
-extern "C" int fq3_set_batch_exact(fq3_engine* e, int32_t on) {
-  if (!e) return fail(FQ3_ERR_INVALID, "null argument");
-  e->kp.batch_exact = on ? 1 : 0;
   return 0;
 }
 

@@ -62,8 +62,7 @@ EXPORTS = [
     "fq3_set_generation_state", "fq3_talker_step", "fq3_predictor_run", "fq3_sample_logits", "fq3_begin_request",
     "fq3_decode_chunk", "fq3_get_past_hidden", "fq3_debug_enable", "fq3_debug_read", "fq3_tape_bytes",
     "fq3_num_ctas", "fq3_launch_count", "fq3_last_error", "fq3_version", "fq3_barrier_test",
-    "fq3_engine_set_prefill_weights", "fq3_prefill", "fq3_set_gemm_backend", "fq3_max_batch", "fq3_set_batch_exact",
-    "fq3_debug_gemv",
+    "fq3_engine_set_prefill_weights", "fq3_prefill", "fq3_set_gemm_backend", "fq3_max_batch", "fq3_debug_gemv",
     "fq3_codec_create", "fq3_codec_load_weights", "fq3_codec_decode", "fq3_codec_decode_batch", "fq3_codec_flops", "fq3_codec_launch_count",
     "fq3_codec_destroy", "fq3_codec_last_error",
 ]
@@ -118,7 +117,6 @@ def load_library() -> C.CDLL:
                                      C.POINTER(ChunkResult), C.c_void_p]
     lib.fq3_get_past_hidden.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
     lib.fq3_max_batch.argtypes = [C.c_void_p]
-    lib.fq3_set_batch_exact.argtypes = [C.c_void_p, C.c_int32]
     lib.fq3_debug_gemv.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.fq3_debug_enable.argtypes = [C.c_void_p, C.c_int32]
     lib.fq3_debug_read.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]
@@ -379,10 +377,6 @@ class Engine:
         out = torch.empty(self.H, dtype=self.dtype, device=self.device)
         _check(self.lib, self.lib.fq3_get_past_hidden(self.h, int(slot), out.data_ptr(), self._stream()))
         return out
-
-    def set_batch_exact(self, on: bool):
-        """batched bf16 GEMVs in the single-sequence kernel's summation order (rows bit-identical to single-slot runs)"""
-        _check(self.lib, self.lib.fq3_set_batch_exact(self.h, int(bool(on))))
 
     def debug_gemv(self, stack: int, layer: int, which: int, x: torch.Tensor) -> torch.Tensor:
         """One batched GEMV over a weight segment (numerics probe): x [ncols,K] -> [ncols, rows] fp32

@@ -177,9 +177,6 @@ int fq3_decode_chunk(fq3_engine* e, const int32_t* slots, int32_t n_slots, int32
 /* last post-norm talker hidden (generate.py:198 past_hidden) of `slot` -> dst_dev [H] model dtype */
 int fq3_get_past_hidden(fq3_engine* e, int32_t slot, void* dst_dev, void* stream);
 int fq3_max_batch(fq3_engine* e);
-/* batched bf16 GEMVs: 0 (default) = fast summation order, 1 = the single-sequence kernel's order (every row of a batched
- * launch then reproduces a single-slot launch bit for bit; also settable with FQ3_BATCH_EXACT=1 at engine creation) */
-int fq3_set_batch_exact(fq3_engine* e, int32_t on);
 /* numerics probe of the batched GEMV: y[col][row] = W_seg[row,:] . x[col,:] for one weight segment of stack 0 (talker) /
  * 1 (predictor): which 0 qkv, 1 o_proj, 2 gate/up (out = model dtype [ncols][I] = silu(gate)*up), 3 down, 4 head
  * (predictor: layer = codebook).  x_dev model dtype [ncols][K]; out_dev float32 [ncols][rows] (which != 2). */

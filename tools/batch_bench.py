@@ -21,7 +21,7 @@ ap.add_argument("--frames", type=int, default=32)
 ap.add_argument("--chunk", type=int, default=8)
 ap.add_argument("--batches", default="1,2,4,8,16,32")
 ap.add_argument("--fp32", action="store_true")
-ap.add_argument("--modes", default="fast", help="comma list of fast,exact (batched bf16 GEMV summation order), measured back to back")
+ap.add_argument("--repeat", type=int, default=1)
 ap.add_argument("--phases", action="store_true", help="clock64 phase accounting of CTA 0 over the last launch")
 a = ap.parse_args()
 Bs = [int(x) for x in a.batches.split(",")]
@@ -30,8 +30,7 @@ cfg = synthetic.make_config(a.size)
 model = FasterQwen3TTS.from_synthetic(a.size, dtype=dt, with_codec=False, max_seq_len=2048, max_batch=max(Bs))
 eng = model.engine
 m = model.model.model
-for B, mode in [(B, md) for B in Bs for md in a.modes.split(",")]:
-    eng.set_batch_exact(mode == "exact")
+for B, mode in [(B, r) for B in Bs for r in range(a.repeat)]:
 
     def run():
         sched = BatchScheduler(eng, m.talker, m.config.talker_config, model.predictor_graph, model.talker_graph)
