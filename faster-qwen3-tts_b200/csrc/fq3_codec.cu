@@ -84,6 +84,231 @@ __global__ void to_channels_last_kernel(const __nv_bfloat16* __restrict__ X, int
   }
 }
 
+
+// ============================================================================================================
+// Front end of the decoder (everything of `speech_tokenizer.decode` before conv_in): RVQ code embedding mean ->
+// sliding-window pre-transformer -> 2 x (ConvTranspose k=s + ConvNeXt).  Dense layers run on the same implicit-GEMM
+// kernel as the stack (taps = 1; fused bias / layer-scale / residual / SwiGLU / GELU epilogues); the kernels below are
+// the row-wise pieces between them.  All activations bf16 channels-last [batch * T][C]; roundings where the torch
+// bf16 modules materialise a tensor.
+// ============================================================================================================
+namespace fe {
+
+__device__ __forceinline__ float rb(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+
+// x[row][:] = mean_q emb[q * codebook + codes[row][q]][:]      one block per (batch, t) row
+__global__ void embed_mean_kernel(const long long* __restrict__ codes, const __nv_bfloat16* __restrict__ emb, int Q,
+                                  int codebook, int H, __nv_bfloat16* __restrict__ X) {
+  const size_t row = blockIdx.x;
+  __shared__ long long ids[64];
+  if ((int)threadIdx.x < Q) {
+    long long c = codes[row * Q + threadIdx.x];
+    c = c < 0 ? 0 : (c >= codebook ? codebook - 1 : c);
+    ids[threadIdx.x] = (long long)threadIdx.x * codebook + c;
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < H; k += blockDim.x) {
+    float s = 0.f;
+    for (int q = 0; q < Q; ++q) s += __bfloat162float(emb[(size_t)ids[q] * H + k]);
+    X[row * H + k] = __float2bfloat16_rn(s / (float)Q);
+  }
+}
+
+// one block (256 threads) per row: Y = w * rnd(x * rsqrt(mean(x^2) + eps))      H <= 2048
+__global__ void rmsnorm_rows_kernel(const __nv_bfloat16* __restrict__ X, const float* __restrict__ w, int H, float eps,
+                                    __nv_bfloat16* __restrict__ Y) {
+  __shared__ float red[8];
+  const size_t row = blockIdx.x;
+  const int tid = threadIdx.x;
+  float v[8];
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int k = tid + i * 256;
+    v[i] = k < H ? __bfloat162float(X[row * H + k]) : 0.f;
+    ss += v[i] * v[i];
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  if ((tid & 31) == 0) red[tid >> 5] = ss;
+  __syncthreads();
+  float tot = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) tot += red[i];
+  const float r = 1.0f / sqrtf(tot / (float)H + eps);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int k = tid + i * 256;
+    if (k < H) Y[row * H + k] = __float2bfloat16_rn(rb(w[k]) * rb(v[i] * r));
+  }
+}
+
+// RoPE in place on the q and k thirds of QKV [rows][3H]; one warp per (row, head, q|k); position = row % T.
+// hd <= 128, rotate_half convention: o[e] = x[e] cos - x[e + hd/2] sin, o[e + hd/2] = x[e + hd/2] cos + x[e] sin
+__global__ void rope_qk_kernel(__nv_bfloat16* __restrict__ QKV, int rows, int T, int nh, int hd,
+                               const float* __restrict__ inv_freq) {
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (gw >= rows * nh * 2) return;
+  const int row = gw / (nh * 2), r = gw % (nh * 2), which = r / nh, h = r % nh;
+  const int H = nh * hd, half = hd >> 1;
+  __nv_bfloat16* p = QKV + (size_t)row * 3 * H + (size_t)which * H + (size_t)h * hd;
+  const float pos = (float)(row % T);
+  for (int e = lane; e < half; e += 32) {
+    const float fr = pos * inv_freq[e];
+    const float cs = rb(cosf(fr)), sn = rb(sinf(fr));
+    const float a = __bfloat162float(p[e]), b = __bfloat162float(p[e + half]);
+    p[e] = __float2bfloat16_rn(rb(a * cs) + rb(-b * sn));
+    p[e + half] = __float2bfloat16_rn(rb(b * cs) + rb(a * sn));
+  }
+}
+
+// causal sliding-window attention (keys j in (i - W, i]) of one head; block = 8 queries (one warp each).
+// QKV [rows][3H] (RoPE applied), OUT [rows][H].  fp32 scores / softmax / P.V.
+template <int HD>
+__global__ void __launch_bounds__(256) swa_kernel(const __nv_bfloat16* __restrict__ QKV, int T, int nh, int W,
+                                                  __nv_bfloat16* __restrict__ OUT) {
+  extern __shared__ float fsm[];
+  const int Wpad = (W + 31) & ~31;
+  float* sc = fsm;                  // [8][Wpad]
+  float* qs = fsm + 8 * Wpad;       // [8][HD]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int i = blockIdx.x * 8 + warp;
+  if (i >= T) return;
+  const int H = nh * HD;
+  const size_t ld = 3 * (size_t)H;
+  const __nv_bfloat16* base = QKV + (size_t)b * T * ld;
+  for (int e = lane; e < HD; e += 32) qs[warp * HD + e] = __bfloat162float(base[(size_t)i * ld + h * HD + e]);
+  __syncwarp();
+  const int lo = max(0, i - W + 1);
+  const int nk = i - lo + 1;
+  const float scale = rsqrtf((float)HD);
+  float* my = sc + warp * Wpad;
+  const float* q = qs + warp * HD;
+  float mx = -INFINITY;
+  for (int jj = lane; jj < nk; jj += 32) {
+    const uint4* kr = reinterpret_cast<const uint4*>(base + (size_t)(lo + jj) * ld + H + h * HD);
+    float d = 0.f;
+#pragma unroll
+    for (int c = 0; c < HD / 8; ++c) {
+      const uint4 w = __ldg(kr + c);
+      const float* qq = q + c * 8;
+      d = fmaf(qq[0], __uint_as_float(w.x << 16), d); d = fmaf(qq[1], __uint_as_float(w.x & 0xffff0000u), d);
+      d = fmaf(qq[2], __uint_as_float(w.y << 16), d); d = fmaf(qq[3], __uint_as_float(w.y & 0xffff0000u), d);
+      d = fmaf(qq[4], __uint_as_float(w.z << 16), d); d = fmaf(qq[5], __uint_as_float(w.z & 0xffff0000u), d);
+      d = fmaf(qq[6], __uint_as_float(w.w << 16), d); d = fmaf(qq[7], __uint_as_float(w.w & 0xffff0000u), d);
+    }
+    d *= scale;
+    my[jj] = d;
+    mx = fmaxf(mx, d);
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  float sum = 0.f;
+  for (int jj = lane; jj < nk; jj += 32) {
+    const float e = expf(my[jj] - mx);
+    my[jj] = e;
+    sum += e;
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  __syncwarp();
+  const float inv = 1.0f / sum;
+  constexpr int EPL = HD / 32;      // dims per lane: [EPL * lane, EPL * lane + EPL)
+  float acc[EPL];
+#pragma unroll
+  for (int e = 0; e < EPL; ++e) acc[e] = 0.f;
+  for (int jj = 0; jj < nk; ++jj) {
+    const float p = my[jj] * inv;
+    const __nv_bfloat16* vr = base + (size_t)(lo + jj) * ld + 2 * H + h * HD + EPL * lane;
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) acc[e] = fmaf(p, __bfloat162float(vr[e]), acc[e]);
+  }
+  __nv_bfloat16* o = OUT + ((size_t)b * T + i) * H + h * HD + EPL * lane;
+#pragma unroll
+  for (int e = 0; e < EPL; ++e) o[e] = __float2bfloat16_rn(acc[e]);
+}
+
+// ConvNeXt head: depthwise causal conv7 (+bias, rounded to bf16 like the conv module's output) followed by
+// LayerNorm(C) with affine parameters.  One block (256 threads) per (batch, t) row; C <= 2048.
+__global__ void dwconv_ln_kernel(const __nv_bfloat16* __restrict__ X, int T, int C, const float* __restrict__ w /*[C][7]*/,
+                                 const float* __restrict__ bias, const float* __restrict__ lnw, const float* __restrict__ lnb,
+                                 float eps, __nv_bfloat16* __restrict__ Y) {
+  __shared__ float red[2][8];
+  const size_t row = blockIdx.x;
+  const int t = (int)(row % T);
+  const int tid = threadIdx.x;
+  float v[8];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = tid + i * 256;
+    v[i] = 0.f;
+    if (c < C) {
+      float a = rb(bias[c]);
+#pragma unroll
+      for (int k = 0; k < 7; ++k) {
+        const int tt = t - 6 + k;
+        if (tt >= 0) a = fmaf(rb(w[c * 7 + k]), __bfloat162float(X[(row - (size_t)(6 - k)) * C + c]), a);
+      }
+      v[i] = rb(a);
+      s += v[i];
+    }
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((tid & 31) == 0) red[0][tid >> 5] = s;
+  __syncthreads();
+  float mean = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) mean += red[0][i];
+  mean /= (float)C;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = tid + i * 256;
+    if (c < C) q += (v[i] - mean) * (v[i] - mean);
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  if ((tid & 31) == 0) red[1][tid >> 5] = q;
+  __syncthreads();
+  float var = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) var += red[1][i];
+  const float r = 1.0f / sqrtf(var / (float)C + eps);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = tid + i * 256;
+    if (c < C) Y[row * C + c] = __float2bfloat16_rn((v[i] - mean) * r * rb(lnw[c]) + rb(lnb[c]));
+  }
+}
+
+}  // namespace fe
+
+struct FeLayer {
+  float *ln1 = nullptr, *ln2 = nullptr, *s1 = nullptr, *s2 = nullptr;
+  __nv_bfloat16 *qkv = nullptr, *o = nullptr, *gu = nullptr, *down = nullptr;
+};
+struct FeUp {
+  int r = 2;
+  __nv_bfloat16 *ct = nullptr, *pw1 = nullptr, *pw2 = nullptr;
+  float *ct_b = nullptr, *dw_w = nullptr, *dw_b = nullptr, *ln_w = nullptr, *ln_b = nullptr, *pw1_b = nullptr,
+        *pw2_b = nullptr, *gamma = nullptr;
+};
+struct FrontEnd {
+  bool ready = false;
+  int Q = 16, codebook = 2048, H = 1024, I = 3072, nh = 16, L = 8, window = 72;
+  float eps = 1e-5f, theta = 10000.f;
+  __nv_bfloat16* emb = nullptr;
+  float *norm = nullptr, *inv_freq = nullptr;
+  std::vector<FeLayer> layers;
+  std::vector<FeUp> ups;
+  size_t cap_rows = 0;
+  __nv_bfloat16* buf[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  double flops_per_frame = 0;
+};
+
 struct Layer {
   int Cin, N, taps, dil, bias_mod, act_mod;  // act_mod 0 => no activated output
   bool write_raw, residual;
@@ -108,6 +333,7 @@ struct fq3_codec {
   int64_t launches = 0;
   double flops_per_frame = 0;
   std::vector<void*> owned;
+  FrontEnd fe;
 };
 
 extern "C" int fq3_codec_create(const int32_t* geom, int32_t n_geom, fq3_codec** out) {
@@ -129,6 +355,7 @@ extern "C" void fq3_codec_destroy(fq3_codec* c) {
   cudaSetDevice(c->dev);
   for (void* p : c->owned) cudaFree(p);
   for (auto* b : c->buf) if (b) cudaFree(b);
+  for (auto* b : c->fe.buf) if (b) cudaFree(b);
   delete c;
 }
 
@@ -276,6 +503,7 @@ static int launch_conv(fq3_codec* c, const Layer& L, const __nv_bfloat16* X, con
   a.X = X; a.W = L.W; a.bias = L.bias; a.R = R; a.Yraw = Yraw; a.Yact = Yact; a.ea = L.ea; a.ib = L.ib;
   a.T = T; a.Cin = L.Cin; a.N = L.N; a.taps = L.taps; a.dil = L.dil; a.bias_mod = L.bias_mod; a.act_mod = L.act_mod;
   a.mode = 0;
+  a.scale = nullptr; a.scale_mod = 1;
   a.batch = batch;
   c->launches++;
   if (g_fq3_gemm_backend == 0) {
@@ -289,14 +517,8 @@ static int launch_conv(fq3_codec* c, const Layer& L, const __nv_bfloat16* X, con
   return 0;
 }
 
-// x_dev: [batch][hidden][T4] bf16 channels-first (output of the front end), pcm_out_dev float32 [batch][T4 * prod(rates)]:
-// `batch` independent windows of equal length share every launch (each with its own causal left padding)
-extern "C" int fq3_codec_decode_batch(fq3_codec* c, const void* x_dev, int32_t batch, int32_t T4, float* pcm_out_dev,
-                                      void* stream_) {
-  if (!c || !x_dev || !pcm_out_dev || T4 <= 0 || batch <= 0) return cfail(FQ3_ERR_INVALID, "null argument");
-  if (c->layers.empty()) return cfail(FQ3_ERR_STATE, "codec weights not loaded");
-  CCK(cudaSetDevice(c->dev));
-  cudaStream_t stream = (cudaStream_t)stream_;
+// the waveform stack on a channels-last bf16 input xcl [batch][T4][hidden]; pcm_out_dev float32 [batch][T4 * prod(rates)]
+static int stack_reserve(fq3_codec* c, int batch, int T4) {
   // largest tensor: [T_final][C_final * 2] worth of bf16 at the widest level; size every buffer for the maximum
   size_t need = (size_t)T4 * c->hidden;
   {
@@ -315,17 +537,16 @@ extern "C" int fq3_codec_decode_batch(fq3_codec* c, const void* x_dev, int32_t b
     for (auto*& b : c->buf) CCK(cudaMalloc(&b, need * 2));
     c->cap = need;
   }
-  {
-    dim3 g((T4 + 31) / 32, (c->hidden + 31) / 32, batch), b(32, 8);
-    to_channels_last_kernel<<<g, b, 0, stream>>>((const __nv_bfloat16*)x_dev, c->hidden, T4, c->buf[0]);
-    c->launches++;
-  }
+  return 0;
+}
+
+static int stack_run(fq3_codec* c, const __nv_bfloat16* xcl, int batch, int T4, float* pcm_out_dev, cudaStream_t stream) {
   int rc;
   int T = T4;
   size_t li = 0;
   // four ping-pong buffers.  `cur` always holds the activated input of the next layer; the other three are free.
   __nv_bfloat16* cur = c->buf[1];
-  if ((rc = launch_conv(c, c->layers[li++], c->buf[0], nullptr, nullptr, cur, T, batch, stream))) return rc;
+  if ((rc = launch_conv(c, c->layers[li++], xcl, nullptr, nullptr, cur, T, batch, stream))) return rc;
   for (int bi = 0; bi < c->n_blocks; ++bi) {
     __nv_bfloat16* f[3];
     int k = 0;
@@ -352,10 +573,252 @@ extern "C" int fq3_codec_decode_batch(fq3_codec* c, const void* x_dev, int32_t b
   return 0;
 }
 
+// x_dev: [batch][hidden][T4] bf16 channels-first (output of a torch front end), pcm_out_dev float32 [batch][T4 * prod(rates)]:
+// `batch` independent windows of equal length share every launch (each with its own causal left padding)
+extern "C" int fq3_codec_decode_batch(fq3_codec* c, const void* x_dev, int32_t batch, int32_t T4, float* pcm_out_dev,
+                                      void* stream_) {
+  if (!c || !x_dev || !pcm_out_dev || T4 <= 0 || batch <= 0) return cfail(FQ3_ERR_INVALID, "null argument");
+  if (c->layers.empty()) return cfail(FQ3_ERR_STATE, "codec weights not loaded");
+  CCK(cudaSetDevice(c->dev));
+  cudaStream_t stream = (cudaStream_t)stream_;
+  int rc;
+  if ((rc = stack_reserve(c, batch, T4))) return rc;
+  {
+    dim3 g((T4 + 31) / 32, (c->hidden + 31) / 32, batch), b(32, 8);
+    to_channels_last_kernel<<<g, b, 0, stream>>>((const __nv_bfloat16*)x_dev, c->hidden, T4, c->buf[0]);
+    c->launches++;
+  }
+  return stack_run(c, c->buf[0], batch, T4, pcm_out_dev, stream);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// front end: weights + the codes -> PCM entry point
+// ------------------------------------------------------------------------------------------------------------
+// dst[(n * dmul + dadd) * K + k] = bf16(src[off + n * sn + k * sk])   (weight repacking on device)
+static __global__ void cast_strided_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long N,
+                                           long long K, long long sn, long long sk, long long off, int dmul, int dadd) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * K) return;
+  const long long n = i / K, k = i - n * K;
+  dst[(n * dmul + dadd) * K + k] = __float2bfloat16_rn(src[off + n * sn + k * sk]);
+}
+
+/* geom = {Q, codebook_size, hidden, intermediate, n_heads, n_layers, sliding_window, n_up, ratio_0 ..};
+ * fgeom = {rms_norm_eps, rope_theta}.  Tensors (float32 on device, PyTorch layouts):
+ *   fe.embed [Q*codebook, H]   fe.norm [H]
+ *   fe.l{i}.ln1 .ln2 .s1 .s2 [H]   .q .k .v .o [H,H]   .gate .up [I,H]   .down [H,I]
+ *   fe.u{i}.ct.w [H,H,r] .ct.b [H]  .dw.w [H,1,7] .dw.b [H]  .ln.w .ln.b [H]  .pw1.w [4H,H] .pw1.b [4H]  .pw2.w [H,4H]
+ *   .pw2.b [H]  .gamma [H] */
+extern "C" int fq3_codec_load_frontend(fq3_codec* c, const int32_t* geom, int32_t n_geom, const float* fgeom,
+                                       int32_t n_fgeom, const fq3_tensor* tensors, int32_t n, void* stream_) {
+  if (!c || !geom || !fgeom || !tensors || n_geom < 8 || n_fgeom < 2) return cfail(FQ3_ERR_INVALID, "null argument");
+  CCK(cudaSetDevice(c->dev));
+  cudaStream_t stream = (cudaStream_t)stream_;
+  FrontEnd& f = c->fe;
+  f.ready = false;
+  f.Q = geom[0]; f.codebook = geom[1]; f.H = geom[2]; f.I = geom[3]; f.nh = geom[4]; f.L = geom[5]; f.window = geom[6];
+  const int n_up = geom[7];
+  if (n_geom < 8 + n_up) return cfail(FQ3_ERR_INVALID, "bad front-end geometry");
+  f.eps = fgeom[0]; f.theta = fgeom[1];
+  const int H = f.H, I = f.I;
+  if (H != c->hidden) return cfail(FQ3_ERR_INVALID, "front-end hidden size differs from the stack's");
+  const int hd = f.nh > 0 ? H / f.nh : 0;
+  if (f.Q < 1 || f.Q > 64 || H % 64 || H > 2048 || I % 32 || f.nh < 1 || hd * f.nh != H || (hd != 64 && hd != 128) ||
+      f.window < 1 || f.L < 0 || n_up < 0)
+    return cfail(FQ3_ERR_INVALID, "front-end geometry unsupported (hidden % 64, head_dim 64/128, Q <= 64)");
+  std::map<std::string, const fq3_tensor*> tm;
+  for (int i = 0; i < n; ++i) tm[tensors[i].name] = &tensors[i];
+  auto find = [&](const std::string& nm, int64_t numel, const float** p) -> int {
+    auto it = tm.find(nm);
+    if (it == tm.end()) return cfail(FQ3_ERR_INVALID, "missing codec tensor ", nm.c_str());
+    if (it->second->numel != numel) return cfail(FQ3_ERR_INVALID, "bad numel for codec tensor ", nm.c_str());
+    *p = (const float*)it->second->dev_ptr;
+    return 0;
+  };
+  auto vec = [&](const std::string& nm, int64_t numel, float** d) -> int {
+    const float* src;
+    int rc = find(nm, numel, &src);
+    if (rc) return rc;
+    CCK(cudaMalloc(d, numel * sizeof(float)));
+    c->owned.push_back(*d);
+    CCK(cudaMemcpyAsync(*d, src, numel * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+    return 0;
+  };
+  auto alloc_bf = [&](int64_t numel, __nv_bfloat16** d) -> int {
+    CCK(cudaMalloc(d, numel * 2));
+    c->owned.push_back(*d);
+    return 0;
+  };
+  auto cast = [&](const std::string& nm, int64_t N, int64_t K, int64_t sn, int64_t sk, int64_t off, int dmul, int dadd,
+                  int64_t src_numel, __nv_bfloat16* dst) -> int {
+    const float* src;
+    int rc = find(nm, src_numel, &src);
+    if (rc) return rc;
+    const long long tot = N * K;
+    cast_strided_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, stream>>>(src, dst, N, K, sn, sk, off, dmul, dadd);
+    CCK(cudaGetLastError());
+    return 0;
+  };
+  int rc;
+  if ((rc = alloc_bf((int64_t)f.Q * f.codebook * H, &f.emb))) return rc;
+  if ((rc = cast("fe.embed", (int64_t)f.Q * f.codebook, H, H, 1, 0, 1, 0, (int64_t)f.Q * f.codebook * H, f.emb))) return rc;
+  if ((rc = vec("fe.norm", H, &f.norm))) return rc;
+  {
+    std::vector<float> inv(hd / 2);
+    for (int i = 0; i < hd / 2; ++i) inv[i] = 1.0f / powf(f.theta, (float)(2 * i) / (float)hd);
+    CCK(cudaMalloc(&f.inv_freq, inv.size() * sizeof(float)));
+    c->owned.push_back(f.inv_freq);
+    CCK(cudaMemcpyAsync(f.inv_freq, inv.data(), inv.size() * sizeof(float), cudaMemcpyHostToDevice, stream));
+    CCK(cudaStreamSynchronize(stream));
+  }
+  f.layers.assign(f.L, FeLayer());
+  double flops = 0;
+  for (int l = 0; l < f.L; ++l) {
+    FeLayer& y = f.layers[l];
+    const std::string p = "fe.l" + std::to_string(l);
+    if ((rc = vec(p + ".ln1", H, &y.ln1)) || (rc = vec(p + ".ln2", H, &y.ln2)) || (rc = vec(p + ".s1", H, &y.s1)) ||
+        (rc = vec(p + ".s2", H, &y.s2)))
+      return rc;
+    if ((rc = alloc_bf((int64_t)3 * H * H, &y.qkv)) || (rc = alloc_bf((int64_t)H * H, &y.o)) ||
+        (rc = alloc_bf((int64_t)2 * I * H, &y.gu)) || (rc = alloc_bf((int64_t)H * I, &y.down)))
+      return rc;
+    const char* qkvn[3] = {".q", ".k", ".v"};
+    for (int j = 0; j < 3; ++j)
+      if ((rc = cast(p + qkvn[j], H, H, H, 1, 0, 1, 0, (int64_t)H * H, y.qkv + (size_t)j * H * H))) return rc;
+    if ((rc = cast(p + ".o", H, H, H, 1, 0, 1, 0, (int64_t)H * H, y.o))) return rc;
+    if ((rc = cast(p + ".gate", I, H, H, 1, 0, 2, 0, (int64_t)I * H, y.gu))) return rc;   // interleaved gate / up rows
+    if ((rc = cast(p + ".up", I, H, H, 1, 0, 2, 1, (int64_t)I * H, y.gu))) return rc;
+    if ((rc = cast(p + ".down", H, I, I, 1, 0, 1, 0, (int64_t)H * I, y.down))) return rc;
+    flops += 2.0 * (4.0 * H * H + 3.0 * H * I);
+  }
+  f.ups.assign(n_up, FeUp());
+  double pos = 1.0;
+  for (int u = 0; u < n_up; ++u) {
+    FeUp& y = f.ups[u];
+    y.r = geom[8 + u];
+    if (y.r < 1 || y.r > 8) return cfail(FQ3_ERR_INVALID, "bad upsampling ratio");
+    const int r = y.r;
+    const std::string p = "fe.u" + std::to_string(u);
+    if ((rc = alloc_bf((int64_t)r * H * H, &y.ct)) || (rc = alloc_bf((int64_t)4 * H * H, &y.pw1)) ||
+        (rc = alloc_bf((int64_t)4 * H * H, &y.pw2)))
+      return rc;
+    // ConvTranspose1d(k = s = r): phase j, output channel co  <-  row j*H + co ;  W'[row][ci] = w[ci][co][j]
+    for (int j = 0; j < r; ++j)
+      if ((rc = cast(p + ".ct.w", H, H, r, (int64_t)H * r, j, 1, j * H, (int64_t)H * H * r, y.ct))) return rc;
+    if ((rc = cast(p + ".pw1.w", 4 * H, H, H, 1, 0, 1, 0, (int64_t)4 * H * H, y.pw1))) return rc;
+    if ((rc = cast(p + ".pw2.w", H, 4 * H, 4 * H, 1, 0, 1, 0, (int64_t)4 * H * H, y.pw2))) return rc;
+    if ((rc = vec(p + ".ct.b", H, &y.ct_b)) || (rc = vec(p + ".dw.w", (int64_t)H * 7, &y.dw_w)) ||
+        (rc = vec(p + ".dw.b", H, &y.dw_b)) || (rc = vec(p + ".ln.w", H, &y.ln_w)) || (rc = vec(p + ".ln.b", H, &y.ln_b)) ||
+        (rc = vec(p + ".pw1.b", 4 * H, &y.pw1_b)) || (rc = vec(p + ".pw2.b", H, &y.pw2_b)) ||
+        (rc = vec(p + ".gamma", H, &y.gamma)))
+      return rc;
+    flops += 2.0 * r * H * H * pos;
+    pos *= r;
+    flops += 2.0 * 8.0 * H * H * pos;
+  }
+  CCK(cudaStreamSynchronize(stream));
+  f.flops_per_frame = flops;
+  CCK(cudaFuncSetAttribute(fe::swa_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+  CCK(cudaFuncSetAttribute(fe::swa_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+  f.ready = true;
+  return 0;
+}
+
+static int fe_gemm(fq3_codec* c, const __nv_bfloat16* X, const __nv_bfloat16* W, const float* bias, const float* scale,
+                   const __nv_bfloat16* R, __nv_bfloat16* Y, int rows, int K, int N, int bias_mod, int mode,
+                   cudaStream_t stream) {
+  ConvArgs a;
+  memset(&a, 0, sizeof(a));
+  a.X = X; a.W = W; a.bias = bias; a.R = R; a.Yraw = Y; a.T = rows; a.Cin = K; a.N = N; a.taps = 1; a.dil = 1;
+  a.bias_mod = bias_mod; a.act_mod = 1; a.mode = mode; a.scale = scale; a.scale_mod = N; a.batch = 1;
+  c->launches++;
+  if (g_fq3_gemm_backend == 0) {
+    const int r = fq3tc::launch_tc(a, stream);
+    if (r == 0) return 0;
+    if (r < 0) return cfail(FQ3_ERR_CUDA, "tcgen05 GEMM launch failed: ", cudaGetErrorString(cudaGetLastError()));
+  }
+  dim3 grid((rows + BM - 1) / BM, (N + BN - 1) / BN);
+  conv_gemm_kernel<<<grid, CTHREADS, CONV_SMEM, stream>>>(a);
+  CCK(cudaGetLastError());
+  return 0;
+}
+
+/* speech_tokenizer.decode (model.py:924,1093,1122) in one call: codes int64 [batch][T][Q] (device) -> PCM float32
+ * [batch][T * total_upsample], clamped to [-1, 1].  `batch` windows of equal length share every launch. */
+extern "C" int fq3_codec_decode_codes(fq3_codec* c, const int64_t* codes_dev, int32_t batch, int32_t T, float* pcm_out_dev,
+                                      void* stream_) {
+  if (!c || !codes_dev || !pcm_out_dev || T <= 0 || batch <= 0) return cfail(FQ3_ERR_INVALID, "null argument");
+  if (c->layers.empty()) return cfail(FQ3_ERR_STATE, "codec weights not loaded");
+  FrontEnd& f = c->fe;
+  if (!f.ready) return cfail(FQ3_ERR_STATE, "fq3_codec_load_frontend has not been called");
+  CCK(cudaSetDevice(c->dev));
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const int H = f.H, I = f.I, hd = H / f.nh;
+  const size_t rows0 = (size_t)batch * T;
+  size_t up = 1;
+  for (auto& u : f.ups) up *= (size_t)u.r;
+  const size_t rowsU = rows0 * up;
+  if (rowsU > f.cap_rows) {
+    for (auto*& b : f.buf) { if (b) cudaFree(b); b = nullptr; }
+    const size_t wide = std::max(rows0 * (size_t)std::max(3 * H, I), rowsU * (size_t)4 * H);
+    for (int i = 0; i < 5; ++i) CCK(cudaMalloc(&f.buf[i], (i == 3 ? wide : rowsU * (size_t)H) * 2));
+    f.cap_rows = rowsU;
+  }
+  int rc;
+  if ((rc = stack_reserve(c, batch, (int)(T * up)))) return rc;
+  __nv_bfloat16 *A = f.buf[0], *Bx = f.buf[1], *Cn = f.buf[2], *D = f.buf[3], *E = f.buf[4];
+  const int R0 = (int)rows0;
+  fe::embed_mean_kernel<<<R0, 256, 0, stream>>>((const long long*)codes_dev, f.emb, f.Q, f.codebook, H, A);
+  c->launches++;
+  const int Wpad = (f.window + 31) & ~31;
+  const size_t swa_smem = (size_t)(8 * Wpad + 8 * hd) * sizeof(float);
+  if (swa_smem > 96 * 1024) return cfail(FQ3_ERR_INVALID, "sliding window too large");
+  for (int l = 0; l < f.L; ++l) {
+    const FeLayer& y = f.layers[l];
+    fe::rmsnorm_rows_kernel<<<R0, 256, 0, stream>>>(A, y.ln1, H, f.eps, Cn);
+    if ((rc = fe_gemm(c, Cn, y.qkv, nullptr, nullptr, nullptr, D, R0, H, 3 * H, 1, 0, stream))) return rc;
+    {
+      const long long warps = (long long)R0 * f.nh * 2;
+      fe::rope_qk_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, stream>>>(D, R0, T, f.nh, hd, f.inv_freq);
+    }
+    {
+      dim3 g((T + 7) / 8, f.nh, batch);
+      if (hd == 64) fe::swa_kernel<64><<<g, 256, swa_smem, stream>>>(D, T, f.nh, f.window, E);
+      else fe::swa_kernel<128><<<g, 256, swa_smem, stream>>>(D, T, f.nh, f.window, E);
+    }
+    if ((rc = fe_gemm(c, E, y.o, nullptr, y.s1, A, Bx, R0, H, H, 1, 0, stream))) return rc;
+    fe::rmsnorm_rows_kernel<<<R0, 256, 0, stream>>>(Bx, y.ln2, H, f.eps, Cn);
+    if ((rc = fe_gemm(c, Cn, y.gu, nullptr, nullptr, nullptr, D, R0, H, 2 * I, 1, 1, stream))) return rc;
+    if ((rc = fe_gemm(c, D, y.down, nullptr, y.s2, Bx, A, R0, I, H, 1, 0, stream))) return rc;
+    c->launches += 4;
+  }
+  fe::rmsnorm_rows_kernel<<<R0, 256, 0, stream>>>(A, f.norm, H, f.eps, Cn);
+  c->launches++;
+  __nv_bfloat16* cur = Cn;
+  int rows = R0, Tc = T;
+  for (size_t u = 0; u < f.ups.size(); ++u) {
+    const FeUp& y = f.ups[u];
+    __nv_bfloat16* out = (cur == Cn) ? E : Cn;
+    // ConvTranspose1d(k = s = r) as a GEMM onto r*H phase channels: [rows][r*H] IS [rows*r][H]
+    if ((rc = fe_gemm(c, cur, y.ct, y.ct_b, nullptr, nullptr, A, rows, H, y.r * H, H, 0, stream))) return rc;
+    rows *= y.r;
+    Tc *= y.r;
+    fe::dwconv_ln_kernel<<<rows, 256, 0, stream>>>(A, Tc, H, y.dw_w, y.dw_b, y.ln_w, y.ln_b, 1e-6f, Bx);
+    c->launches++;
+    if ((rc = fe_gemm(c, Bx, y.pw1, y.pw1_b, nullptr, nullptr, D, rows, H, 4 * H, 4 * H, 2, stream))) return rc;
+    if ((rc = fe_gemm(c, D, y.pw2, y.pw2_b, y.gamma, A, out, rows, 4 * H, H, H, 0, stream))) return rc;
+    cur = out;
+  }
+  CCK(cudaGetLastError());
+  return stack_run(c, cur, batch, Tc, pcm_out_dev, stream);
+}
+
 extern "C" int fq3_codec_decode(fq3_codec* c, const void* x_dev, int32_t T4, float* pcm_out_dev, void* stream_) {
   return fq3_codec_decode_batch(c, x_dev, 1, T4, pcm_out_dev, stream_);
 }
 
 extern "C" double fq3_codec_flops(fq3_codec* c, int32_t T4) { return c ? c->flops_per_frame * T4 : 0.0; }
+/* front end FLOPs for T code frames (dense layers only) */
+extern "C" double fq3_codec_frontend_flops(fq3_codec* c, int32_t T) { return c ? c->fe.flops_per_frame * T : 0.0; }
 extern "C" int64_t fq3_codec_launch_count(fq3_codec* c) { return c ? c->launches : 0; }
 extern "C" const char* fq3_codec_last_error(void) { return g_cerr; }

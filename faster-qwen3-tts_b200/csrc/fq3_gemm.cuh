@@ -3,7 +3,9 @@
 // 128 x 96 x 32 tiles, 8 warps (2 x 4), bf16 mma.sync m16n8k16 / fp32 accumulation, ldmatrix from XOR-swizzled
 // shared memory, 4-stage cp.async pipeline.  Epilogue (all roundings where torch would materialise a bf16 tensor):
 //   mode 0: v = rnd(acc + bias); if R: v = rnd(v + R); Yraw <- v; Yact <- SnakeBeta(v)
+//           with `scale`: v = rnd(acc + bias) * scale[n] before the residual add (layer scale / ConvNeXt gamma)
 //   mode 1: SwiGLU on adjacent column pairs (gate, up): Yraw[t, n/2] = rnd(rnd(silu(rnd(g))) * rnd(u))
+//   mode 2: mode 0 with an exact (erf) GELU applied to rnd(acc + bias) first
 #pragma once
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -25,7 +27,9 @@ struct ConvArgs {
   const float* ea;          // exp(alpha) [act_mod]
   const float* ib;          // 1 / (exp(beta) + 1e-9) [act_mod]
   int T, Cin, N, taps, dil, bias_mod, act_mod;
-  int mode;                 // 0 general, 1 SwiGLU pair epilogue (Yraw is [T][N/2])
+  int mode;                 // 0 general, 1 SwiGLU pair epilogue (Yraw is [T][N/2]), 2 general with GELU
+  const float* scale;       // per-column factor [scale_mod] applied to rnd(acc + bias) before the residual, or null
+  int scale_mod;
   int batch;                // independent sequences: X is [batch][T][Cin], R / Yraw / Yact are [batch][T][N]; every
                             // sequence has its own causal left padding (0 or 1 = a single sequence)
 };
@@ -51,6 +55,7 @@ __device__ __forceinline__ void mma16816(float* d, const uint32_t* a, uint32_t b
       : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 // swizzled byte offset of (row, 16-byte chunk) inside a [rows][32 bf16] tile
 __device__ __forceinline__ int swz(int row, int chunk) { return row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4); }
 
@@ -168,6 +173,14 @@ static __global__ void __launch_bounds__(CTHREADS, 2) conv_gemm_kernel(  // stat
         if (a.bias) {
           v0 += a.bias[n % a.bias_mod];
           v1 += a.bias[(n + 1) % a.bias_mod];
+        }
+        if (a.mode == 2) {
+          v0 = gelu_erf(__bfloat162float(__float2bfloat16_rn(v0)));
+          v1 = gelu_erf(__bfloat162float(__float2bfloat16_rn(v1)));
+        }
+        if (a.scale) {
+          v0 = __bfloat162float(__float2bfloat16_rn(v0)) * a.scale[n % a.scale_mod];
+          v1 = __bfloat162float(__float2bfloat16_rn(v1)) * a.scale[(n + 1) % a.scale_mod];
         }
         const size_t off = ybase + (size_t)m * a.N + n;
         if (a.R) {  // torch: conv/linear output is a bf16 tensor, THEN the residual add (second rounding)

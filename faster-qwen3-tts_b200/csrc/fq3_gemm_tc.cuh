@@ -14,6 +14,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <mutex>
+#include <unordered_map>
+
 #include "fq3_gemm.cuh"
 
 namespace fq3tc {
@@ -29,7 +32,7 @@ struct Cfg {
   static constexpr int B_BYTES = TBN * BK * 2;
   static constexpr int STAGE = A_BYTES + B_BYTES;
   static constexpr int STAGES = DEEP ? (BK == 64 ? 7 : 12) : (BK == 64 ? 3 : 4);
-  static constexpr int SMEM = STAGES * STAGE + 1024 /*align slack*/ + 256 /*barriers*/ + 3 * TBN * 4 /*epilogue params*/;
+  static constexpr int SMEM = STAGES * STAGE + 1024 /*align slack*/ + 256 /*barriers*/ + 4 * TBN * 4 /*epilogue params*/;
   static constexpr uint32_t SBO = (8 * BK * 2) >> 4;          // 8-row group stride, 16-byte units
   static constexpr uint64_t LAYOUT = BK == 64 ? 2ull : 4ull;  // SWIZZLE_128B : SWIZZLE_64B
 };
@@ -101,7 +104,7 @@ static __global__ void __launch_bounds__(TTHREADS, DEEP ? 1 : 2)
   uint64_t* empty = full + C::STAGES;
   uint64_t* accum = empty + C::STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum + 1);
-  float* ep = reinterpret_cast<float*>(tiles + C::STAGES * C::STAGE + 256);  // [3][TBN]: bias, exp(alpha), 1/(exp(beta)+eps)
+  float* ep = reinterpret_cast<float*>(tiles + C::STAGES * C::STAGE + 256);  // [4][TBN]: bias, exp(alpha), 1/(exp(beta)+eps), scale
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_m = (a.T + TBM - 1) / TBM;
   const int bidx = blockIdx.x / tiles_m;   // sequence of the batch (own causal padding: TMA zero-fills rows < 0 of ITS time axis)
@@ -162,10 +165,11 @@ static __global__ void __launch_bounds__(TTHREADS, DEEP ? 1 : 2)
     // loads on the critical path after the accumulator is ready)
     for (int i = threadIdx.x - 64; i < TBN; i += 128) {
       const int n = n0 + i;
-      const bool ok = n < a.N && a.mode == 0;
+      const bool ok = n < a.N && a.mode != 1;
       ep[i] = (ok && a.bias) ? a.bias[n % a.bias_mod] : 0.f;
       ep[TBN + i] = (ok && a.Yact) ? a.ea[n % a.act_mod] : 0.f;
       ep[2 * TBN + i] = (ok && a.Yact) ? a.ib[n % a.act_mod] : 0.f;
+      ep[3 * TBN + i] = (ok && a.scale) ? a.scale[n % a.scale_mod] : 1.f;
     }
     asm volatile("bar.sync 1, 128;" ::: "memory");
     mb_wait(accum, 0);
@@ -207,6 +211,14 @@ static __global__ void __launch_bounds__(TTHREADS, DEEP ? 1 : 2)
             for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[j][h * 8 + i]);
 #pragma unroll
             for (int i = 0; i < 8; ++i) v[i] += ep[j * 32 + h * 8 + i];
+            if (a.mode == 2) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[i] = fq3gemm::gelu_erf(__bfloat162float(__float2bfloat16_rn(v[i])));
+            }
+            if (a.scale) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[i] = __bfloat162float(__float2bfloat16_rn(v[i])) * ep[3 * TBN + j * 32 + h * 8 + i];
+            }
             if (a.R) {
               const uint4 rr = *reinterpret_cast<const uint4*>(a.R + off + j * 32 + h * 8);
               const __nv_bfloat16* rb = reinterpret_cast<const __nv_bfloat16*>(&rr);
@@ -282,6 +294,43 @@ static bool make_map3(CUtensorMap* tm, const void* base, uint64_t batch, uint64_
             CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// Tensor maps are pure functions of (base, shape, box): encode each distinct one ONCE and reuse it on every later
+// launch (weights and the engine's activation buffers keep their addresses), so a launch costs no driver call.
+struct MapKey {
+  const void* base;
+  uint64_t batch, rows, cols;
+  uint32_t box_rows, box_cols;
+  bool operator==(const MapKey& o) const {
+    return base == o.base && batch == o.batch && rows == o.rows && cols == o.cols && box_rows == o.box_rows && box_cols == o.box_cols;
+  }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    uint64_t h = (uint64_t)(uintptr_t)k.base * 0x9e3779b97f4a7c15ull;
+    h ^= (k.rows + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2));
+    h ^= (k.cols * 1315423911ull + (h << 6) + (h >> 2));
+    h ^= ((k.batch << 40) ^ ((uint64_t)k.box_rows << 20) ^ k.box_cols) + (h << 6) + (h >> 2);
+    return (size_t)h;
+  }
+};
+static bool cached_map(CUtensorMap* tm, const void* base, uint64_t batch /*0: 2-D*/, uint64_t rows, uint64_t cols,
+                       uint32_t box_rows, uint32_t box_cols) {
+  static std::mutex mu;
+  static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
+  const MapKey key{base, batch, rows, cols, box_rows, box_cols};
+  std::lock_guard<std::mutex> lk(mu);
+  auto it = cache.find(key);
+  if (it != cache.end()) {
+    *tm = it->second;
+    return true;
+  }
+  const bool ok = batch ? make_map3(tm, base, batch, rows, cols, box_rows, box_cols) : make_map(tm, base, rows, cols, box_rows, box_cols);
+  if (!ok) return false;
+  if (cache.size() > 16384) cache.clear();
+  cache.emplace(key, *tm);
+  return true;
+}
+
 // returns 0 on success, 1 if this shape must use the mma.sync fallback, <0 on CUDA error
 static int launch_tc(const fq3gemm::ConvArgs& a, cudaStream_t stream) {
   static bool attr_done = false;
@@ -302,8 +351,8 @@ static int launch_tc(const fq3gemm::ConvArgs& a, cudaStream_t stream) {
   if (a.mode == 1 ? (a.N % 32 != 0) : (a.N % 8 != 0)) return 1;
   CUtensorMap tmX, tmW;
   const int nb = a.batch > 1 ? a.batch : 1;
-  if (!make_map3(&tmX, a.X, (uint64_t)nb, (uint64_t)a.T, (uint64_t)a.Cin, TBM, BK)) return 1;
-  if (!make_map(&tmW, a.W, (uint64_t)a.N, (uint64_t)a.taps * a.Cin, TBN, BK)) return 1;
+  if (!cached_map(&tmX, a.X, (uint64_t)nb, (uint64_t)a.T, (uint64_t)a.Cin, TBM, BK)) return 1;
+  if (!cached_map(&tmW, a.W, 0, (uint64_t)a.N, (uint64_t)a.taps * a.Cin, TBN, BK)) return 1;
   dim3 grid(((a.T + TBM - 1) / TBM) * nb, (a.N + TBN - 1) / TBN);
   const bool deep = (long long)grid.x * grid.y <= (long long)num_sms * 3 / 2;
   if (BK == 64) {

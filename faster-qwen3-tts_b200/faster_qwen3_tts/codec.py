@@ -11,9 +11,10 @@ convs :3283-3330, ConvNeXt :3333-3366, SnakeBeta :3645-3683, decoder block :3705
 conv7, SnakeBeta, conv1)] with r = 8,5,4,3 and channels 1536->768->384->192->96 -> SnakeBeta -> conv7 -> clamp.
 Total upsample 1920.  "parity unpinned" (analogue geometry, synthetic weights).
 
-Round 1: the module below is the torch-library implementation (cuDNN / cuBLAS), used as the functional baseline
-and as the weight container; the sm_100a kernels replace its hot layers through the C ABI as they land
-(kernel K4).
+The torch module below is the weight container and the library (cuDNN / cuBLAS) functional baseline
+(``backend="torch"``).  ``backend="engine"`` -- the default on CUDA -- runs the WHOLE decode, codes in / PCM out, in
+the hand-written sm_100a kernels behind the C ABI (``fq3_codec_decode_codes``, csrc/fq3_codec.cu): no library kernel
+is launched (kernel K4).
 """
 from __future__ import annotations
 
@@ -212,12 +213,14 @@ class SpeechTokenizer:
     """The decode side of the upstream speech tokenizer, as the reference consumes it
     (``decode({"audio_codes": [B,T,16]}) -> ([wav], sample_rate)``).
 
-    backend="engine": the waveform stack (conv_in, 4 upsampling blocks, conv_out: 94% of the decoder FLOPs) runs in
-    the hand-written sm_100a kernels of csrc/fq3_codec.cu through the C ABI; the light front end (code embedding,
-    8-layer pre-transformer, 2 x (ConvTranspose k=2 + ConvNeXt)) stays in torch, captured once per window length in a
-    CUDA graph.  backend="torch": the plain library implementation (functional baseline)."""
+    backend="engine": codes -> PCM entirely in the hand-written sm_100a kernels of csrc/fq3_codec.cu through the C
+    ABI: front end (code-embedding mean, 8-layer sliding-window pre-transformer, 2 x (ConvTranspose k=2 + ConvNeXt))
+    and waveform stack (conv_in, 4 upsampling blocks, conv_out) -- ``fq3_codec_decode_codes``.
+    ``native_front=False`` (or FQ3_CODEC_TORCH_FRONT=1) keeps the round-1 split for A/B runs: front end as torch ops
+    (CUDA-graphed per window length), stack in the engine.  backend="torch": the plain library implementation."""
 
-    def __init__(self, decoder: Code2Wav, backend: str = "torch", graph_front: bool = True):
+    def __init__(self, decoder: Code2Wav, backend: str = "torch", graph_front: bool = True, native_front: bool = None):
+        import os
         self.decoder = decoder
         self.sample_rate = decoder.config.sample_rate
         self.launches = 0
@@ -226,8 +229,11 @@ class SpeechTokenizer:
         self._h = None
         self._graphs = {}
         self._seen = {}
+        self.native_front = (os.environ.get("FQ3_CODEC_TORCH_FRONT", "0") != "1") if native_front is None else native_front
         if backend == "engine":
             self._init_engine()
+            if self.native_front:
+                self._init_frontend()
 
     # ---- engine plumbing -------------------------------------------------------------------------------
     def _init_engine(self):
@@ -269,6 +275,44 @@ class SpeechTokenizer:
             if lib.fq3_codec_load_weights(h, arr_t, len(t), C.c_void_p(torch.cuda.current_stream(self._dev).cuda_stream)):
                 raise RuntimeError(lib.fq3_codec_last_error().decode())
         self._h = h
+
+    def _init_frontend(self):
+        import ctypes as C
+        from .engine import Tensor
+        d, lib = self.decoder, self._lib
+        c = d.config
+        t = {}
+
+        def put(name, x):
+            t[name] = x.detach().to(torch.float32).contiguous()
+
+        put("fe.embed", d.code_embedding.weight)
+        put("fe.norm", d.norm.weight)
+        for i, l in enumerate(d.layers):
+            p = f"fe.l{i}"
+            put(p + ".ln1", l.ln1.weight); put(p + ".ln2", l.ln2.weight); put(p + ".s1", l.s1); put(p + ".s2", l.s2)
+            put(p + ".q", l.q.weight); put(p + ".k", l.k.weight); put(p + ".v", l.v.weight); put(p + ".o", l.o.weight)
+            put(p + ".gate", l.gate.weight); put(p + ".up", l.up.weight); put(p + ".down", l.down.weight)
+        for i, (up, nx) in enumerate(d.upsample):
+            p = f"fe.u{i}"
+            put(p + ".ct.w", up.conv.weight); put(p + ".ct.b", up.conv.bias)
+            put(p + ".dw.w", nx.dwconv.conv.weight); put(p + ".dw.b", nx.dwconv.conv.bias)
+            put(p + ".ln.w", nx.norm.weight); put(p + ".ln.b", nx.norm.bias)
+            put(p + ".pw1.w", nx.pwconv1.weight); put(p + ".pw1.b", nx.pwconv1.bias)
+            put(p + ".pw2.w", nx.pwconv2.weight); put(p + ".pw2.b", nx.pwconv2.bias)
+            put(p + ".gamma", nx.gamma)
+        geom = [c.num_quantizers, c.codebook_size, c.hidden_size, c.intermediate_size, c.num_attention_heads,
+                c.num_hidden_layers, c.sliding_window, len(c.upsampling_ratios)] + list(c.upsampling_ratios)
+        g = (C.c_int32 * len(geom))(*geom)
+        fg = (C.c_float * 2)(c.rms_norm_eps, c.rope_theta)
+        arr_t = (Tensor * len(t))()
+        for i, (k, v) in enumerate(t.items()):
+            arr_t[i] = Tensor(k.encode(), v.data_ptr(), v.numel())
+        with torch.cuda.device(self._dev):
+            if lib.fq3_codec_load_frontend(self._h, g, len(geom), fg, 2, arr_t, len(t),
+                                           C.c_void_p(torch.cuda.current_stream(self._dev).cuda_stream)):
+                raise RuntimeError(lib.fq3_codec_last_error().decode())
+            torch.cuda.current_stream(self._dev).synchronize()
 
     def __del__(self):
         try:
@@ -333,6 +377,20 @@ class SpeechTokenizer:
     def decode(self, payload) -> Tuple[List[torch.Tensor], int]:
         codes = payload["audio_codes"]  # [B, T, Q]
         dev = next(self.decoder.parameters()).device
+        if self.backend == "engine" and self.native_front:
+            import ctypes as C
+            codes = codes.to(device=dev, dtype=torch.long).contiguous()
+            B, T, Q = codes.shape
+            if Q != self.decoder.config.num_quantizers:
+                raise ValueError(f"audio_codes must have {self.decoder.config.num_quantizers} code groups, got {Q}")
+            pcm = torch.empty(B, T * self.decoder.config.total_upsample, dtype=torch.float32, device=dev)
+            with torch.cuda.device(dev):
+                rc = self._lib.fq3_codec_decode_codes(self._h, C.c_void_p(codes.data_ptr()), B, T, C.c_void_p(pcm.data_ptr()),
+                                                      C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+            if rc:
+                raise RuntimeError(self._lib.fq3_codec_last_error().decode())
+            self.launches = int(self._lib.fq3_codec_launch_count(self._h))
+            return [pcm[b] for b in range(B)], self.sample_rate
         codes = codes.to(dev).transpose(1, 2).contiguous()
         if self.backend != "engine":
             wav = self.decoder(codes)
@@ -354,7 +412,11 @@ class SpeechTokenizer:
         return [pcm[b] for b in range(B)], self.sample_rate
 
     def flops(self, T: int) -> float:
+        """dense-layer FLOPs of the waveform stack for T code frames"""
         return float(self._lib.fq3_codec_flops(self._h, 4 * T)) if self._h is not None else 0.0
+
+    def frontend_flops(self, T: int) -> float:
+        return float(self._lib.fq3_codec_frontend_flops(self._h, T)) if self._h is not None else 0.0
 
 
 def build_codec(cfg: Code2WavConfig = None, seed: int = 0, dtype=torch.bfloat16, device="cpu",

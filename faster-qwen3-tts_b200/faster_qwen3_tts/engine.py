@@ -63,7 +63,8 @@ EXPORTS = [
     "fq3_decode_chunk", "fq3_get_past_hidden", "fq3_debug_enable", "fq3_debug_read", "fq3_tape_bytes",
     "fq3_num_ctas", "fq3_launch_count", "fq3_last_error", "fq3_version", "fq3_barrier_test",
     "fq3_engine_set_prefill_weights", "fq3_prefill", "fq3_set_gemm_backend", "fq3_max_batch", "fq3_debug_gemv",
-    "fq3_codec_create", "fq3_codec_load_weights", "fq3_codec_decode", "fq3_codec_decode_batch", "fq3_codec_flops", "fq3_codec_launch_count",
+    "fq3_codec_create", "fq3_codec_load_weights", "fq3_codec_decode", "fq3_codec_decode_batch", "fq3_codec_flops",
+    "fq3_codec_load_frontend", "fq3_codec_decode_codes", "fq3_codec_frontend_flops", "fq3_codec_launch_count",
     "fq3_codec_destroy", "fq3_codec_last_error",
 ]
 
@@ -133,6 +134,11 @@ def load_library() -> C.CDLL:
     lib.fq3_codec_load_weights.argtypes = [C.c_void_p, C.POINTER(Tensor), C.c_int32, C.c_void_p]
     lib.fq3_codec_decode.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
     lib.fq3_codec_decode_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
+    lib.fq3_codec_load_frontend.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_float), C.c_int32,
+                                            C.POINTER(Tensor), C.c_int32, C.c_void_p]
+    lib.fq3_codec_decode_codes.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
+    lib.fq3_codec_frontend_flops.argtypes = [C.c_void_p, C.c_int32]
+    lib.fq3_codec_frontend_flops.restype = C.c_double
     lib.fq3_codec_flops.argtypes = [C.c_void_p, C.c_int32]
     lib.fq3_codec_flops.restype = C.c_double
     lib.fq3_codec_launch_count.argtypes = [C.c_void_p]

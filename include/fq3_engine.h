@@ -207,7 +207,19 @@ int fq3_codec_decode(fq3_codec* c, const void* x_dev, int32_t T4, float* pcm_out
 /* `batch` windows of equal length in one set of launches (concurrent requests, BASELINE config 4): x_dev bf16
  * [batch][hidden][T4], pcm float32 [batch][T4*prod(rates)]; every window has its own causal left padding. */
 int fq3_codec_decode_batch(fq3_codec* c, const void* x_dev, int32_t batch, int32_t T4, float* pcm_out_dev, void* stream);
+/* The decoder's front end -- everything of speech_tokenizer.decode before conv_in: 16-codebook embedding mean,
+ * sliding-window pre-transformer (RMSNorm, RoPE, layer scale, SwiGLU), 2 x (ConvTranspose k=s + ConvNeXt) -- as
+ * hand-written kernels + the same tcgen05 GEMM.  geom = {Q, codebook_size, hidden, intermediate, n_heads, n_layers,
+ * sliding_window, n_up, ratio_0 ..}; fgeom = {rms_norm_eps, rope_theta}.  Tensor names / layouts: csrc/fq3_codec.cu. */
+int fq3_codec_load_frontend(fq3_codec* c, const int32_t* geom, int32_t n_geom, const float* fgeom, int32_t n_fgeom,
+                            const fq3_tensor* tensors, int32_t n, void* stream);
+/* speech_tokenizer.decode({"audio_codes": [batch,T,16]}) (model.py:924,1093,1122):
+ * codes_dev int64 [batch][T][Q] -> pcm float32 [batch][T * total_upsample] clamped to [-1,1].  No library kernel is
+ * launched.  Requires fq3_codec_load_weights + fq3_codec_load_frontend. */
+int fq3_codec_decode_codes(fq3_codec* c, const int64_t* codes_dev, int32_t batch, int32_t T, float* pcm_out_dev,
+                           void* stream);
 double fq3_codec_flops(fq3_codec* c, int32_t T4);
+double fq3_codec_frontend_flops(fq3_codec* c, int32_t T);
 int64_t fq3_codec_launch_count(fq3_codec* c);
 void fq3_codec_destroy(fq3_codec* c);
 const char* fq3_codec_last_error(void);

@@ -83,3 +83,53 @@ def test_streaming_windows_end_to_end_codes_to_pcm(full_codec):
         worst = max(worst, err)
         print(f"chunk {ci}: max|d| = {err:.3e}")
     assert worst < TOL
+
+
+def test_native_front_end_agrees_with_torch_front_end(full_codec):
+    """codes -> PCM entirely in the engine (fq3_codec_decode_codes) against the round-1 split (torch-library front end
+    feeding the engine's waveform stack): same weights, same codes; both are bf16 pipelines of the same function."""
+    from faster_qwen3_tts.codec import SpeechTokenizer
+    st = full_codec
+    assert st.native_front
+    split = SpeechTokenizer(st.decoder, backend="engine", graph_front=False, native_front=False)
+    for T in (5, 33, 100):
+        codes = torch.randint(0, 2048, (1, T, 16), generator=torch.Generator().manual_seed(100 + T)).cuda()
+        a, _ = st.decode({"audio_codes": codes})
+        b, _ = split.decode({"audio_codes": codes})
+        err = (a[0] - b[0]).abs().max().item()
+        print(f"T={T}: max|native - split| = {err:.3e}")
+        assert err < TOL
+
+
+def test_batched_windows_bit_identical_to_single_windows(full_codec):
+    """`batch` windows of equal length in one call: every row equals its own single-window decode bit for bit (each
+    window keeps its own causal left padding / attention window / RoPE positions)."""
+    st = full_codec
+    codes = torch.randint(0, 2048, (3, 33, 16), generator=torch.Generator().manual_seed(9)).cuda()
+    both, _ = st.decode({"audio_codes": codes})
+    for b in range(3):
+        one, _ = st.decode({"audio_codes": codes[b:b + 1]})
+        assert torch.equal(one[0], both[b]), b
+
+
+def test_engine_decode_launches_no_library_kernel(full_codec):
+    """Every kernel of a decode call comes from libfq3_engine.so (no cuDNN / cuBLAS / ATen kernel): names via the
+    torch profiler (CUPTI); skipped when the profiler cannot trace CUDA here."""
+    st = full_codec
+    codes = torch.randint(0, 2048, (1, 33, 16), generator=torch.Generator().manual_seed(1)).cuda()
+    st.decode({"audio_codes": codes})
+    torch.cuda.synchronize()
+    try:
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            st.decode({"audio_codes": codes})
+            torch.cuda.synchronize()
+        names = [e.key for e in prof.key_averages() if getattr(e, "device_type", None) is not None and "Memcpy" not in e.key and "Memset" not in e.key]
+    except Exception as ex:  # pragma: no cover
+        pytest.skip(f"CUDA profiling unavailable: {ex!r}")
+    kernels = [n for n in names if "kernel" in n or "(" in n]
+    if not kernels:
+        pytest.skip("profiler returned no kernel records")
+    print(sorted(set(kernels)))
+    foreign = [n for n in kernels if not any(s in n for s in ("fe::", "conv_gemm", "conv_out_kernel", "fq3", "cast_strided"))]
+    assert not foreign, foreign
