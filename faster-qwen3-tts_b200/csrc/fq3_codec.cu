@@ -506,8 +506,8 @@ static int launch_conv(fq3_codec* c, const Layer& L, const __nv_bfloat16* X, con
   a.scale = nullptr; a.scale_mod = 1;
   a.batch = batch;
   c->launches++;
-  if (g_fq3_gemm_backend == 0) {
-    const int r = fq3tc::launch_tc(a, stream);
+  if (g_fq3_gemm_backend != 1) {
+    const int r = fq3tc::launch_tc(a, stream, g_fq3_gemm_backend);
     if (r == 0) return 0;
     if (r < 0) return cfail(FQ3_ERR_CUDA, "tcgen05 conv launch failed: ", cudaGetErrorString(cudaGetLastError()));
   }
@@ -732,8 +732,8 @@ static int fe_gemm(fq3_codec* c, const __nv_bfloat16* X, const __nv_bfloat16* W,
   a.X = X; a.W = W; a.bias = bias; a.R = R; a.Yraw = Y; a.T = rows; a.Cin = K; a.N = N; a.taps = 1; a.dil = 1;
   a.bias_mod = bias_mod; a.act_mod = 1; a.mode = mode; a.scale = scale; a.scale_mod = N; a.batch = 1;
   c->launches++;
-  if (g_fq3_gemm_backend == 0) {
-    const int r = fq3tc::launch_tc(a, stream);
+  if (g_fq3_gemm_backend != 1) {
+    const int r = fq3tc::launch_tc(a, stream, g_fq3_gemm_backend);
     if (r == 0) return 0;
     if (r < 0) return cfail(FQ3_ERR_CUDA, "tcgen05 GEMM launch failed: ", cudaGetErrorString(cudaGetLastError()));
   }

@@ -114,7 +114,7 @@ struct fq3_engine {
 
 int g_fq3_gemm_backend = 0;  // shared with fq3_codec.cu
 extern "C" int fq3_set_gemm_backend(int32_t backend) {
-  g_fq3_gemm_backend = backend ? 1 : 0;
+  g_fq3_gemm_backend = backend == 2 ? 2 : (backend ? 1 : 0);
   return 0;
 }
 

@@ -93,6 +93,76 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
       : "r"(taddr));
 }
 
+// epilogue of one accumulator row (r: 96 fp32 columns of output row m of sequence bidx, columns n0..n0+95);
+// ep: [4][TBN] staged bias / exp(alpha) / 1/(exp(beta)+eps) / scale of these columns
+__device__ __forceinline__ void tc_epilogue_row(const fq3gemm::ConvArgs& a, const float* ep, uint32_t (&r)[3][32], int m,
+                                                int bidx, int n0) {
+if (m < a.T) {
+  if (a.mode == 1) {
+    __nv_bfloat16* dst = a.Yraw + ((size_t)bidx * a.T + m) * (a.N >> 1) + (n0 >> 1);
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      __align__(16) __nv_bfloat16 o[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const float gte = __bfloat162float(__float2bfloat16_rn(__uint_as_float(r[j][2 * i])));
+        const float up = __bfloat162float(__float2bfloat16_rn(__uint_as_float(r[j][2 * i + 1])));
+        const float sl = __bfloat162float(__float2bfloat16_rn(gte / (1.0f + expf(-gte))));
+        o[i] = __float2bfloat16_rn(sl * up);
+      }
+      if (n0 + j * 32 < a.N) {
+        *reinterpret_cast<uint4*>(dst + j * 16) = *reinterpret_cast<const uint4*>(o);
+        *reinterpret_cast<uint4*>(dst + j * 16 + 8) = *reinterpret_cast<const uint4*>(o + 8);
+      }
+    }
+  } else {
+    const size_t off = ((size_t)bidx * a.T + m) * a.N + n0;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+#pragma unroll
+      for (int h = 0; h < 4; ++h) {  // 8 columns at a time (16-byte vectors)
+        const int n = n0 + j * 32 + h * 8;
+        if (n >= a.N) continue;
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[j][h * 8 + i]);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] += ep[j * 32 + h * 8 + i];
+        if (a.mode == 2) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[i] = fq3gemm::gelu_erf(__bfloat162float(__float2bfloat16_rn(v[i])));
+        }
+        if (a.scale) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[i] = __bfloat162float(__float2bfloat16_rn(v[i])) * ep[3 * TBN + j * 32 + h * 8 + i];
+        }
+        if (a.R) {
+          const uint4 rr = *reinterpret_cast<const uint4*>(a.R + off + j * 32 + h * 8);
+          const __nv_bfloat16* rb = reinterpret_cast<const __nv_bfloat16*>(&rr);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[i] = __bfloat162float(__float2bfloat16_rn(v[i])) + __bfloat162float(rb[i]);
+        }
+        __align__(16) __nv_bfloat16 raw[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) raw[i] = __float2bfloat16_rn(v[i]);
+        if (a.Yraw) *reinterpret_cast<uint4*>(a.Yraw + off + j * 32 + h * 8) = *reinterpret_cast<const uint4*>(raw);
+        if (a.Yact) {
+          __align__(16) __nv_bfloat16 act[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float x = __bfloat162float(raw[i]);
+            const int cidx = j * 32 + h * 8 + i;
+            const float sn = __sinf(x * ep[TBN + cidx]);
+            act[i] = __float2bfloat16_rn(x + ep[2 * TBN + cidx] * sn * sn);
+          }
+          *reinterpret_cast<uint4*>(a.Yact + off + j * 32 + h * 8) = *reinterpret_cast<const uint4*>(act);
+        }
+      }
+    }
+  }
+}
+}
+
 template <int BK, int DEEP>
 static __global__ void __launch_bounds__(TTHREADS, DEEP ? 1 : 2)
     conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
@@ -180,76 +250,146 @@ static __global__ void __launch_bounds__(TTHREADS, DEEP ? 1 : 2)
 #pragma unroll
     for (int j = 0; j < 3; ++j) tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * 32), r[j]);
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-    if (m < a.T) {
-      if (a.mode == 1) {
-        __nv_bfloat16* dst = a.Yraw + ((size_t)bidx * a.T + m) * (a.N >> 1) + (n0 >> 1);
-#pragma unroll
-        for (int j = 0; j < 3; ++j) {
-          __align__(16) __nv_bfloat16 o[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float gte = __bfloat162float(__float2bfloat16_rn(__uint_as_float(r[j][2 * i])));
-            const float up = __bfloat162float(__float2bfloat16_rn(__uint_as_float(r[j][2 * i + 1])));
-            const float sl = __bfloat162float(__float2bfloat16_rn(gte / (1.0f + expf(-gte))));
-            o[i] = __float2bfloat16_rn(sl * up);
-          }
-          if (n0 + j * 32 < a.N) {
-            *reinterpret_cast<uint4*>(dst + j * 16) = *reinterpret_cast<const uint4*>(o);
-            *reinterpret_cast<uint4*>(dst + j * 16 + 8) = *reinterpret_cast<const uint4*>(o + 8);
-          }
-        }
-      } else {
-        const size_t off = ((size_t)bidx * a.T + m) * a.N + n0;
-#pragma unroll
-        for (int j = 0; j < 3; ++j) {
-#pragma unroll
-          for (int h = 0; h < 4; ++h) {  // 8 columns at a time (16-byte vectors)
-            const int n = n0 + j * 32 + h * 8;
-            if (n >= a.N) continue;
-            float v[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[j][h * 8 + i]);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] += ep[j * 32 + h * 8 + i];
-            if (a.mode == 2) {
-#pragma unroll
-              for (int i = 0; i < 8; ++i) v[i] = fq3gemm::gelu_erf(__bfloat162float(__float2bfloat16_rn(v[i])));
-            }
-            if (a.scale) {
-#pragma unroll
-              for (int i = 0; i < 8; ++i) v[i] = __bfloat162float(__float2bfloat16_rn(v[i])) * ep[3 * TBN + j * 32 + h * 8 + i];
-            }
-            if (a.R) {
-              const uint4 rr = *reinterpret_cast<const uint4*>(a.R + off + j * 32 + h * 8);
-              const __nv_bfloat16* rb = reinterpret_cast<const __nv_bfloat16*>(&rr);
-#pragma unroll
-              for (int i = 0; i < 8; ++i) v[i] = __bfloat162float(__float2bfloat16_rn(v[i])) + __bfloat162float(rb[i]);
-            }
-            __align__(16) __nv_bfloat16 raw[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) raw[i] = __float2bfloat16_rn(v[i]);
-            if (a.Yraw) *reinterpret_cast<uint4*>(a.Yraw + off + j * 32 + h * 8) = *reinterpret_cast<const uint4*>(raw);
-            if (a.Yact) {
-              __align__(16) __nv_bfloat16 act[8];
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const float x = __bfloat162float(raw[i]);
-                const int cidx = j * 32 + h * 8 + i;
-                const float sn = __sinf(x * ep[TBN + cidx]);
-                act[i] = __float2bfloat16_rn(x + ep[2 * TBN + cidx] * sn * sn);
-              }
-              *reinterpret_cast<uint4*>(a.Yact + off + j * 32 + h * 8) = *reinterpret_cast<const uint4*>(act);
-            }
-          }
-        }
-      }
-    }
+    tc_epilogue_row(a, ep, r, m, bidx, n0);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   }
   __syncthreads();
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TMEM_COLS) : "memory");
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------------------------
+// Persistent variant: one CTA per SM walks a strided list of output tiles; the fp32 accumulator is DOUBLE-BUFFERED in
+// TMEM (2 x 128 columns), so the epilogue of tile i (tcgen05.ld -> bias / residual / SnakeBeta -> stores) runs while
+// the TMA / MMA warps are already in the main loop of tile i+1; barriers, TMEM and the descriptor prefetch are paid
+// once per CTA instead of once per tile, and the smem ring never drains between tiles.  Tile order: M fastest, so the
+// CTAs running concurrently share one weight tile (L2 / TMA locality).
+// ------------------------------------------------------------------------------------------------------------
+template <int BK>
+struct PCfg {
+  static constexpr int A_BYTES = TBM * BK * 2;
+  static constexpr int B_BYTES = TBN * BK * 2;
+  static constexpr int STAGE = A_BYTES + B_BYTES;
+  static constexpr int STAGES = BK == 64 ? 6 : 10;
+  static constexpr int SMEM = STAGES * STAGE + 1024 /*align slack*/ + 512 /*barriers*/ + 4 * TBN * 4 /*epilogue params*/;
+  static constexpr uint32_t SBO = (8 * BK * 2) >> 4;
+  static constexpr uint64_t LAYOUT = BK == 64 ? 2ull : 4ull;
+};
+constexpr int PTMEM_COLS = 256;
+
+template <int BK>
+static __global__ void __launch_bounds__(TTHREADS, 1)
+    conv_gemm_tcp_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
+                         const __grid_constant__ fq3gemm::ConvArgs a, const int tiles_m, const int tiles_mb, const int ntiles) {
+  using C = PCfg<BK>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = reinterpret_cast<uint64_t*>(tiles + C::STAGES * C::STAGE);
+  uint64_t* empty = full + C::STAGES;
+  uint64_t* accf = empty + C::STAGES;   // [2] accumulator buffer complete (MMA -> epilogue)
+  uint64_t* acce = accf + 2;            // [2] accumulator buffer drained (epilogue -> MMA)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acce + 2);
+  float* ep = reinterpret_cast<float*>(tiles + C::STAGES * C::STAGE + 512);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kc = a.Cin / BK, nks = a.taps * kc;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < C::STAGES; ++i) { mb_init(&full[i], 1); mb_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mb_init(&accf[i], 1); mb_init(&acce[i], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmX) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(su32(tmem_slot)), "n"(PTMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int nt = tile / tiles_mb, mb = tile - nt * tiles_mb;
+        const int bidx = mb / tiles_m, m0 = (mb - bidx * tiles_m) * TBM, n0 = nt * TBN;
+        for (int ks = 0; ks < nks; ++ks, ++it) {
+          const int s = (int)(it % C::STAGES);
+          mb_wait(&empty[s], ((it / C::STAGES) & 1u) ^ 1u);
+          const int tap = ks / kc, c0 = (ks - tap * kc) * BK;
+          const int shift = (a.taps - 1 - tap) * a.dil;
+          uint8_t* A = tiles + s * C::STAGE;
+          mb_expect(&full[s], C::STAGE);
+          tma_load_3d(A, &tmX, c0, m0 - shift, bidx, &full[s]);
+          tma_load_2d(A + C::A_BYTES, &tmW, tap * a.Cin + c0, n0, &full[s]);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TBN >> 3) << 17) | ((uint32_t)(TBM >> 4) << 24);
+      uint32_t it = 0, j = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++j) {
+        const uint32_t b = j & 1u;
+        mb_wait(&acce[b], ((j >> 1) & 1u) ^ 1u);     // the epilogue has drained this accumulator buffer
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t tacc = tmem + b * 128u;
+        for (int ks = 0; ks < nks; ++ks, ++it) {
+          const int s = (int)(it % C::STAGES);
+          mb_wait(&full[s], (it / C::STAGES) & 1u);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint8_t* A = tiles + s * C::STAGE;
+          const uint64_t da = smem_desc(A, C::SBO, C::LAYOUT), db = smem_desc(A + C::A_BYTES, C::SBO, C::LAYOUT);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)
+            umma_bf16(tacc, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (ks | k) ? 1u : 0u);
+          umma_commit(&empty[s]);
+        }
+        umma_commit(&accf[b]);
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int q = warp & 3;
+    uint32_t j = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++j) {
+      const int nt = tile / tiles_mb, mb = tile - nt * tiles_mb;
+      const int bidx = mb / tiles_m, m0 = (mb - bidx * tiles_m) * TBM, n0 = nt * TBN;
+      asm volatile("bar.sync 1, 128;" ::: "memory");   // everyone is done with the previous tile's parameters
+      for (int i = threadIdx.x - 64; i < TBN; i += 128) {
+        const int n = n0 + i;
+        const bool ok = n < a.N && a.mode != 1;
+        ep[i] = (ok && a.bias) ? a.bias[n % a.bias_mod] : 0.f;
+        ep[TBN + i] = (ok && a.Yact) ? a.ea[n % a.act_mod] : 0.f;
+        ep[2 * TBN + i] = (ok && a.Yact) ? a.ib[n % a.act_mod] : 0.f;
+        ep[3 * TBN + i] = (ok && a.scale) ? a.scale[n % a.scale_mod] : 1.f;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const uint32_t b = j & 1u;
+      mb_wait(&accf[b], (j >> 1) & 1u);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      uint32_t r[3][32];
+#pragma unroll
+      for (int jj = 0; jj < 3; ++jj) tmem_ld32(tmem + b * 128u + ((uint32_t)(q * 32) << 16) + (uint32_t)(jj * 32), r[jj]);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(su32(&acce[b])) : "memory");
+      tc_epilogue_row(a, ep, r, m0 + q * 32 + lane, bidx, n0);
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(PTMEM_COLS) : "memory");
   }
 }
 
@@ -332,7 +472,8 @@ static bool cached_map(CUtensorMap* tm, const void* base, uint64_t batch /*0: 2-
 }
 
 // returns 0 on success, 1 if this shape must use the mma.sync fallback, <0 on CUDA error
-static int launch_tc(const fq3gemm::ConvArgs& a, cudaStream_t stream) {
+// variant: 0 = persistent kernel when a CTA would get more than one tile (default), 2 = always one tile per CTA
+static int launch_tc(const fq3gemm::ConvArgs& a, cudaStream_t stream, int variant = 0) {
   static bool attr_done = false;
   static int num_sms = 148;
   if (!attr_done) {
@@ -340,6 +481,8 @@ static int launch_tc(const fq3gemm::ConvArgs& a, cudaStream_t stream) {
     if (cudaFuncSetAttribute(conv_gemm_tc_kernel<32, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<32, 0>::SMEM) != cudaSuccess) return -1;
     if (cudaFuncSetAttribute(conv_gemm_tc_kernel<64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<64, 1>::SMEM) != cudaSuccess) return -1;
     if (cudaFuncSetAttribute(conv_gemm_tc_kernel<32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<32, 1>::SMEM) != cudaSuccess) return -1;
+    if (cudaFuncSetAttribute(conv_gemm_tcp_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, PCfg<64>::SMEM) != cudaSuccess) return -1;
+    if (cudaFuncSetAttribute(conv_gemm_tcp_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, PCfg<32>::SMEM) != cudaSuccess) return -1;
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
@@ -354,6 +497,13 @@ static int launch_tc(const fq3gemm::ConvArgs& a, cudaStream_t stream) {
   if (!cached_map(&tmX, a.X, (uint64_t)nb, (uint64_t)a.T, (uint64_t)a.Cin, TBM, BK)) return 1;
   if (!cached_map(&tmW, a.W, 0, (uint64_t)a.N, (uint64_t)a.taps * a.Cin, TBN, BK)) return 1;
   dim3 grid(((a.T + TBM - 1) / TBM) * nb, (a.N + TBN - 1) / TBN);
+  const long long ntiles = (long long)grid.x * grid.y;
+  if (variant == 0 && ntiles > num_sms && ntiles < (1ll << 30)) {
+    const int tiles_m = (a.T + TBM - 1) / TBM;
+    if (BK == 64) conv_gemm_tcp_kernel<64><<<num_sms, TTHREADS, PCfg<64>::SMEM, stream>>>(tmX, tmW, a, tiles_m, tiles_m * nb, (int)ntiles);
+    else conv_gemm_tcp_kernel<32><<<num_sms, TTHREADS, PCfg<32>::SMEM, stream>>>(tmX, tmW, a, tiles_m, tiles_m * nb, (int)ntiles);
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+  }
   const bool deep = (long long)grid.x * grid.y <= (long long)num_sms * 3 / 2;
   if (BK == 64) {
     if (deep) conv_gemm_tc_kernel<64, 1><<<grid, TTHREADS, Cfg<64, 1>::SMEM, stream>>>(tmX, tmW, a);

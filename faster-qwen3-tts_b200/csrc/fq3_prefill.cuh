@@ -167,8 +167,8 @@ static int pf_gemm(fq3_engine* e, const __nv_bfloat16* X, const __nv_bfloat16* W
   a.X = X; a.W = W; a.R = R; a.Yraw = Y; a.T = T; a.Cin = K; a.N = N; a.taps = 1; a.dil = 1;
   a.bias_mod = 1; a.act_mod = 1; a.mode = mode;
   e->launches++;
-  if (g_fq3_gemm_backend == 0) {
-    const int r = fq3tc::launch_tc(a, stream);
+  if (g_fq3_gemm_backend != 1) {
+    const int r = fq3tc::launch_tc(a, stream, g_fq3_gemm_backend);
     if (r == 0) return 0;
     if (r < 0) return fail(FQ3_ERR_CUDA, "tcgen05 GEMM launch failed: %s", cudaGetErrorString(cudaGetLastError()));
   }

@@ -149,8 +149,10 @@ def load_library() -> C.CDLL:
 
 
 def set_gemm_backend(name: str):
-    """'tcgen05' (default) or 'mma' for the dense layers of K3 (prefill) and K4 (codec)."""
-    load_library().fq3_set_gemm_backend(0 if name == "tcgen05" else 1)
+    """Dense layers of K3 (prefill) and K4 (codec): 'tcgen05' (default: persistent tile loop with a double-buffered TMEM
+    accumulator whenever a CTA gets more than one tile), 'tcgen05_1tile' (one tile per CTA, the round-1 kernel) or 'mma'
+    (mma.sync kernel) -- the last two for A/B runs."""
+    load_library().fq3_set_gemm_backend({"tcgen05": 0, "mma": 1, "tcgen05_1tile": 2}[name])
 
 
 class EngineError(RuntimeError):

@@ -556,14 +556,19 @@ class FasterQwen3TTS:
                                        ref_codes=None, voice_clone_prompt=None
                                        ) -> Generator[Tuple[np.ndarray, int, dict], None, None]:
         self._reject_ggml_cached_reference_args(ref_spk, ref_rvq, ref_spk_emb, ref_codes)
-        if parity_mode:
-            raise NotImplementedError("parity_mode streams through upstream qwen-tts's dynamic-cache generate, which "
-                                      "is absent offline")
         nsm = self._resolve_non_streaming_mode(non_streaming_mode, default=False)
         m, talker, config, tie, tam, tth, tpe, ref_codes = self._prepare_generation(
             text=text, language=language, ref_audio=ref_audio, ref_text=ref_text, xvec_only=xvec_only,
             non_streaming_mode=nsm, append_silence=append_silence, voice_clone_prompt=voice_clone_prompt,
             instruct=instruct)
+        if parity_mode:   # the reference's dynamic-cache baseline (model.py:1064-1077 -> streaming.py:192-359)
+            from .streaming import parity_generate_streaming
+            chunks = parity_generate_streaming(
+                talker=talker, talker_input_embeds=tie, attention_mask=tam, trailing_text_hiddens=tth, tts_pad_embed=tpe,
+                config=config, max_new_tokens=max_new_tokens, min_new_tokens=min_new_tokens, temperature=temperature,
+                top_k=top_k, top_p=top_p, do_sample=do_sample, repetition_penalty=repetition_penalty, chunk_size=chunk_size)
+            yield from self._stream_audio(chunks, m.speech_tokenizer, ref_codes, chunk_size)
+            return
         yield from self.stream_from_embeds(tie, tam, tth, tpe, ref_codes=ref_codes, chunk_size=chunk_size,
                                            max_new_tokens=max_new_tokens, min_new_tokens=min_new_tokens,
                                            temperature=temperature, top_k=top_k, top_p=top_p, do_sample=do_sample,

@@ -25,7 +25,7 @@ recorded, which pins suppress/temperature/top-k/top-p/softmax bit for bit.
                                    policy, model.py:1052-1135) with request preparation, token stream and codec
                                    decoder replaced by deterministic doubles (oracle/window_cases.py)
 
-Usage:  python oracle/make_golden.py            (writes tests/golden/{sampling,loop,prompt,window}.npz)
+Usage:  python oracle/make_golden.py            (writes tests/golden/{sampling,loop,prompt,window,parity_stream}.npz)
 """
 from __future__ import annotations
 
@@ -351,6 +351,33 @@ def gen_window(out_path):
     np.savez_compressed(out_path, **out)
 
 
+# ----------------------------------------------------------------------------------------------
+# parity (dynamic-cache) streaming fixtures: the reference's own parity_generate_streaming, driven with the decode-step
+# talker double of oracle/parity_cases.py (torch.multinomial seeded; the probabilities it is handed are pinned bit for
+# bit by sampling.npz)
+# ----------------------------------------------------------------------------------------------
+def gen_parity_stream(ref, out_path):
+    from oracle import parity_cases as PC
+    torch.cuda.synchronize = lambda *a, **k: None  # streaming.py:262,337,353
+    out = {}
+    for case in PC.CASES:
+        chunks, timings, calls = PC.run_case(ref["streaming"].parity_generate_streaming, case)
+        name = case[0]
+        codes = torch.cat(chunks) if chunks else torch.zeros(0, 16, dtype=torch.long)
+        out[name + "_codes"] = codes.numpy()
+        out[name + "_chunks"] = np.array([c.shape[0] for c in chunks], dtype=np.int64)
+        out[name + "_final"] = np.array([int(t["is_final"]) for t in timings], dtype=np.int64)
+        out[name + "_total"] = np.array([t["total_steps_so_far"] for t in timings], dtype=np.int64)
+        out[name + "_ncalls"] = np.array([len(calls)], dtype=np.int64)
+        out[name + "_lastcall"] = np.array([str(calls[-1])])
+        keys = sorted(timings[0].keys()) if timings else []
+        print(f"parity {name}: frames={codes.shape[0]} chunks={[c.shape[0] for c in chunks]} final={[int(t['is_final']) for t in timings]} "
+              f"calls={len(calls)} keys={keys}")
+    out["names"] = np.array([c[0] for c in PC.CASES])
+    out["timing_keys"] = np.array(sorted(timings[0].keys()))
+    np.savez_compressed(out_path, **out)
+
+
 if __name__ == "__main__":
     ref = load_reference()
     gdir = os.path.join(ROOT, "tests", "golden")
@@ -360,3 +387,4 @@ if __name__ == "__main__":
         gen_loop(ref, os.path.join(gdir, "loop.npz"))
         gen_prompt(os.path.join(gdir, "prompt.npz"))
         gen_window(os.path.join(gdir, "window.npz"))
+        gen_parity_stream(ref, os.path.join(gdir, "parity_stream.npz"))

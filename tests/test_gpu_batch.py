@@ -47,12 +47,16 @@ def _left_padded_batch(cfg, lens, Tt_list, seed, dtype):
 
 def _oracle_rows(p, tie, tam, tth, tpe, uniforms, sp_t, sp_p, max_new, min_new, max_seq_len):
     want = []
+    # tiny tensors: intra-op threading only adds synchronisation (a 32-row oracle run took minutes on a many-core box)
+    nthr = torch.get_num_threads()
+    torch.set_num_threads(1)
     for b in range(tie.shape[0]):
         pad = int((tam[b] == 0).sum())
         with torch.inference_mode():
             want.append(O.generate(p.om, tie[b], tth[b], tpe, max_new_tokens=max_new[b] if isinstance(max_new, list) else max_new,
                                    min_new_tokens=min_new, sp_talker=sp_t, sp_pred=sp_p, max_seq_len=max_seq_len,
                                    uniforms=None if uniforms is None else uniforms[b], n_left_pad=pad))
+    torch.set_num_threads(nthr)
     return want
 
 
