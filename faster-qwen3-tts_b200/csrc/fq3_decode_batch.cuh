@@ -863,17 +863,21 @@ __device__ __noinline__ void producer_batch_main(const KParams& P) {
     for (int f = 0; P.mode != MODE_GEMV_TEST && f < P.n_frames && !pr.stopped; ++f) {
       if (P.has_mtp) rep(P.seg_mtp, nb2, true);
       for (int i = 0; i < P.ncb; ++i) {
+        if ((i == 0 ? nb2 : nb1) == 1) pr.pf_range(P.p.seg_base, P.p.seg_base + 4 * P.p.L - 1);
+        else pr.pf_ptr = nullptr;   // replayed segments: no run-ahead
         for (int l = 0; l < P.p.L; ++l)
           for (int q = 0; q < 4; ++q) rep(P.p.seg_base + 4 * l + q, i == 0 ? nb2 : nb1, l < P.pred_pin_layers);
         rep(P.p.seg_head + i, nb1, false);
       }
+      if (nb1 == 1) pr.pf_range(P.t.seg_base, P.t.seg_head);
+      else pr.pf_ptr = nullptr;
       for (int l = 0; l < P.t.L; ++l)
         for (int q = 0; q < 4; ++q) rep(P.t.seg_base + 4 * l + q, nb1, false);
       rep(P.t.seg_head, nb1, false);
     }
-    s.prod_issued = (int)pr.ctr;
+    flag_st(&s.prod_issued, (int)pr.ctr);
     __threadfence_block();
-    s.prod_done = 1;
+    flag_st(&s.prod_done, 1);
   }
 }
 
@@ -1100,12 +1104,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) fq3_decode_batch_kernel(const __g
     // ---- drain: stop the producer and wait for every bulk copy it has in flight
     csync();
     if (tid == 0) {
-      s.stop_flag = 1;
+      flag_st(&s.stop_flag, 1);
       __threadfence_block();
-      while (!s.prod_done) {
+      while (!flag_ld(&s.prod_done)) {
       }
       __threadfence_block();
-      const uint32_t issued = (uint32_t)s.prod_issued;
+      const uint32_t issued = (uint32_t)flag_ld(&s.prod_issued);
       for (uint32_t t = c.tile_ctr; t < issued; ++t) mbar_wait(&s.full[t % NS], (t / NS) & 1u);
     }
     csync();
