@@ -66,6 +66,7 @@ def parse():
     ap.add_argument("--no-codec", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-reference", action="store_true")
+    ap.add_argument("--no-stateful", action="store_true", help="skip the extra legs with the stateful streaming codec")
     ap.add_argument("--batch", type=int, default=32, help="config 4: concurrent requests per GPU (0/1 disables the leg)")
     ap.add_argument("--batch-prompt", type=int, default=40)
     ap.add_argument("--batch-steps", type=int, default=2)
@@ -332,6 +333,22 @@ def run_b200(args):
     ms = ev0.elapsed_time(ev1)
     launches = eng.launch_count + model.codec_launches() - l0
     clk = clocks.stop() if rank == 0 else None
+    # ---- extra leg: the same request with the STATEFUL streaming codec (not the headline: its
+    # Phase-2 audio is the non-streaming decode rather than the reference's 25-frame-context windows)
+    sc = None
+    if not args.no_codec and not args.no_stateful:
+        model.streaming_codec = "stateful"
+        step_resident(False)
+        n0, k0 = len(ttfa_ms), len(chunk_ms)
+        barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        fr_s = sum(step_resident(True) for _ in range(args.steps))
+        s1.record()
+        barrier()
+        sc = {"ms": s0.elapsed_time(s1), "frames": fr_s, "ttfa_ms_p50": statistics.median(ttfa_ms[n0:])}
+        del ttfa_ms[n0:], chunk_ms[k0:]
+        model.streaming_codec = "window"
     # ---- e2e leg
     model._voice_prompt_cache.clear()
     step_e2e()   # one untimed pass (lazy allocations of the prompt path)
@@ -352,8 +369,8 @@ def run_b200(args):
     if B4:
         c4 = run_config4(args, model, cfg, dev, rank, barrier)
     from faster_qwen3_tts.replicas import aggregate
-    vals = [ms, e_s * 1000] + ([c4["ms_decode"], c4["ms_codec"]] if c4 else [])
-    cnts = [frames, e_frames] + ([c4["frames_decode"], c4["frames_codec"]] if c4 else [])
+    vals = [ms, e_s * 1000] + ([c4["ms_decode"], c4["ms_codec"], c4["ms_stateful"]] if c4 else [0.0, 0.0, 0.0]) + [sc["ms"] if sc else 0.0]
+    cnts = [frames, e_frames] + ([c4["frames_decode"], c4["frames_codec"], c4["frames_stateful"]] if c4 else [0, 0, 0]) + [sc["frames"] if sc else 0]
     mx, sm = aggregate(vals, cnts, device=dev)
     ms, e_ms = mx[0], mx[1]
     frames, e_frames = sm[0], sm[1]
@@ -453,6 +470,7 @@ def run_b200(args):
                         f"uniforms per request; batched persistent kernel (one launch per chunk for all requests)",
             "requests_per_gpu": B4, "n_gpus": world,
             "rtf_aggregate_decode": fd * FRAME_S / (md / 1000), "rtf_aggregate_with_codec": fc * FRAME_S / (mc / 1000) if mc else None,
+            "rtf_aggregate_with_stateful_codec": sm[4] * FRAME_S / (mx[4] / 1000) if mx[4] else None,
             "ms_per_frame_step": kms / args.chunk if kms else None,
             "speedup_vs_batch1_decode": (fd * FRAME_S / (md / 1000)) / (value * 1.0) if value else None,
             "roofline": {"bound": "hbm", "kernel": "fq3_decode_batch_kernel<bf16> (one launch = one chunk of all requests)",
@@ -460,6 +478,11 @@ def run_b200(args):
                          "alg_bytes_per_step": bytes_step, "launch_ms": kms,
                          "note": "weights once per step + KV of every row; frac measures HBM use, aggregate RTF the gain"},
         }
+    if sc:
+        out["stateful_codec"] = {
+            "what": "same request, streaming_codec='stateful' (fq3_codec_stream_decode: every chunk costs its own 8 frames; "
+                    "audio = the non-streaming decode; the ICL reference frames warm the stream state before the first chunk)",
+            "rtf": sm[5] * FRAME_S / (mx[5] / 1000) if mx[5] else None, "ttfa_ms_p50_rank0": sc["ttfa_ms_p50"]}
     if not args.no_gpu_reference and not args.no_codec:
         try:
             out["gpu_reference"] = run_gpu_reference(args, model, cfg, dev, (tie, tam, tth, tpe), ref_codes)
@@ -534,8 +557,21 @@ def run_config4(args, model, cfg, dev, rank, barrier):
         e1.record()
         barrier()
         ms_c = e0.elapsed_time(e1)
-    return {"ms_decode": ms_d, "frames_decode": fd, "ms_codec": ms_c, "frames_codec": fc,
-            "kernel_ms": statistics.mean(kms) if kms else None, "P": Pm, "lens": (min(lens), max(lens))}
+    ms_s, fs = 0.0, 0
+    if not args.no_codec and not args.no_stateful:
+        model.streaming_codec = "stateful"
+        run(True)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.batch_steps):
+            fs += run(True)
+        e1.record()
+        barrier()
+        ms_s = e0.elapsed_time(e1)
+        model.streaming_codec = "window"
+    return {"ms_decode": ms_d, "frames_decode": fd, "ms_codec": ms_c, "frames_codec": fc, "ms_stateful": ms_s,
+            "frames_stateful": fs, "kernel_ms": statistics.mean(kms) if kms else None, "P": Pm, "lens": (min(lens), max(lens))}
 
 
 def run_gpu_reference(args, model, cfg, dev, prompt, ref_codes):

@@ -46,14 +46,14 @@ using namespace fq3gemm;
 
 // final causal conv7 (C -> 1) over activated input + clamp to [-1, 1]; one thread per output sample
 __global__ void conv_out_kernel(const __nv_bfloat16* __restrict__ X, const float* __restrict__ W, float bias, int T,
-                                int C, int taps, float* __restrict__ out) {
+                                int C, int taps, float* __restrict__ out, int x_row0, int x_rows) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= T) return;
-  X += (size_t)blockIdx.y * T * C;      // blockIdx.y = sequence of the batch
+  X += (size_t)blockIdx.y * x_rows * C;  // blockIdx.y = sequence of the batch; its input has x_row0 history rows in front
   out += (size_t)blockIdx.y * T;
   float s = bias;
   for (int k = 0; k < taps; ++k) {
-    const int tt = t - (taps - 1 - k);
+    const int tt = x_row0 + t - (taps - 1 - k);
     if (tt < 0) continue;
     const __nv_bfloat162* x = reinterpret_cast<const __nv_bfloat162*>(X + (size_t)tt * C);
     const float* w = W + (size_t)k * C;
@@ -146,13 +146,13 @@ __global__ void rmsnorm_rows_kernel(const __nv_bfloat16* __restrict__ X, const f
 // RoPE in place on the q and k thirds of QKV [rows][3H]; one warp per (row, head, q|k); position = row % T.
 // hd <= 128, rotate_half convention: o[e] = x[e] cos - x[e + hd/2] sin, o[e + hd/2] = x[e + hd/2] cos + x[e] sin
 __global__ void rope_qk_kernel(__nv_bfloat16* __restrict__ QKV, int rows, int T, int nh, int hd,
-                               const float* __restrict__ inv_freq) {
+                               const float* __restrict__ inv_freq, const int* __restrict__ pos0) {
   const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (gw >= rows * nh * 2) return;
   const int row = gw / (nh * 2), r = gw % (nh * 2), which = r / nh, h = r % nh;
   const int H = nh * hd, half = hd >> 1;
   __nv_bfloat16* p = QKV + (size_t)row * 3 * H + (size_t)which * H + (size_t)h * hd;
-  const float pos = (float)(row % T);
+  const float pos = (float)((row % T) + (pos0 ? pos0[row / T] : 0));   // streaming: frames this sequence has seen before
   for (int e = lane; e < half; e += 32) {
     const float fr = pos * inv_freq[e];
     const float cs = rb(cosf(fr)), sn = rb(sinf(fr));
@@ -164,9 +164,12 @@ __global__ void rope_qk_kernel(__nv_bfloat16* __restrict__ QKV, int rows, int T,
 
 // causal sliding-window attention (keys j in (i - W, i]) of one head; block = 8 queries (one warp each).
 // QKV [rows][3H] (RoPE applied), OUT [rows][H].  fp32 scores / softmax / P.V.
+// Streaming: every sequence's QKV block has x_rows = row0 + T rows, the first row0 of them the cached (k, v) rows of
+// earlier chunks, of which only the last valid[b] exist yet.
 template <int HD>
 __global__ void __launch_bounds__(256) swa_kernel(const __nv_bfloat16* __restrict__ QKV, int T, int nh, int W,
-                                                  __nv_bfloat16* __restrict__ OUT) {
+                                                  __nv_bfloat16* __restrict__ OUT, int x_rows, int row0,
+                                                  const int* __restrict__ valid) {
   extern __shared__ float fsm[];
   const int Wpad = (W + 31) & ~31;
   float* sc = fsm;                  // [8][Wpad]
@@ -177,11 +180,12 @@ __global__ void __launch_bounds__(256) swa_kernel(const __nv_bfloat16* __restric
   if (i >= T) return;
   const int H = nh * HD;
   const size_t ld = 3 * (size_t)H;
-  const __nv_bfloat16* base = QKV + (size_t)b * T * ld;
-  for (int e = lane; e < HD; e += 32) qs[warp * HD + e] = __bfloat162float(base[(size_t)i * ld + h * HD + e]);
+  const __nv_bfloat16* base = QKV + (size_t)b * x_rows * ld;
+  const int ie = row0 + i;                                   // row of query i inside the sequence's block
+  for (int e = lane; e < HD; e += 32) qs[warp * HD + e] = __bfloat162float(base[(size_t)ie * ld + h * HD + e]);
   __syncwarp();
-  const int lo = max(0, i - W + 1);
-  const int nk = i - lo + 1;
+  const int lo = max(row0 - (valid ? valid[b] : row0), ie - W + 1);
+  const int nk = ie - lo + 1;
   const float scale = rsqrtf((float)HD);
   float* my = sc + warp * Wpad;
   const float* q = qs + warp * HD;
@@ -233,10 +237,11 @@ __global__ void __launch_bounds__(256) swa_kernel(const __nv_bfloat16* __restric
 // LayerNorm(C) with affine parameters.  One block (256 threads) per (batch, t) row; C <= 2048.
 __global__ void dwconv_ln_kernel(const __nv_bfloat16* __restrict__ X, int T, int C, const float* __restrict__ w /*[C][7]*/,
                                  const float* __restrict__ bias, const float* __restrict__ lnw, const float* __restrict__ lnb,
-                                 float eps, __nv_bfloat16* __restrict__ Y) {
+                                 float eps, __nv_bfloat16* __restrict__ Y, int x_row0, int x_rows) {
   __shared__ float red[2][8];
   const size_t row = blockIdx.x;
-  const int t = (int)(row % T);
+  const int t = (int)(row % T) + x_row0;                                  // row inside the sequence's input block
+  const size_t xrow = (row / T) * (size_t)x_rows + t;
   const int tid = threadIdx.x;
   float v[8];
   float s = 0.f;
@@ -249,7 +254,7 @@ __global__ void dwconv_ln_kernel(const __nv_bfloat16* __restrict__ X, int T, int
 #pragma unroll
       for (int k = 0; k < 7; ++k) {
         const int tt = t - 6 + k;
-        if (tt >= 0) a = fmaf(rb(w[c * 7 + k]), __bfloat162float(X[(row - (size_t)(6 - k)) * C + c]), a);
+        if (tt >= 0) a = fmaf(rb(w[c * 7 + k]), __bfloat162float(X[(xrow - (size_t)(6 - k)) * C + c]), a);
       }
       v[i] = rb(a);
       s += v[i];
@@ -334,6 +339,22 @@ struct fq3_codec {
   double flops_per_frame = 0;
   std::vector<void*> owned;
   FrontEnd fe;
+  // ---- stateful streaming (fq3_codec_stream_*): causal sites in execution order
+  struct Site { int h, C; size_t off; };   // history rows / channels of the site's INPUT tensor, offset into a stream's tails
+  std::vector<Site> sites;
+  size_t tail_elems = 0;
+  __nv_bfloat16* ext = nullptr;            // [batch][h + T][C] work buffer of the site being executed
+  size_t ext_cap = 0;
+  void** d_tailptr = nullptr;              // device copies of the per-call stream tables
+  int* d_pos0 = nullptr;
+  int* d_valid = nullptr;
+  int tab_cap = 0;
+};
+
+struct fq3_codec_stream {
+  fq3_codec* owner = nullptr;
+  __nv_bfloat16* tails = nullptr;          // history rows of every causal site (zero = before the stream started)
+  long long frames = 0;                    // code frames decoded so far
 };
 
 extern "C" int fq3_codec_create(const int32_t* geom, int32_t n_geom, fq3_codec** out) {
@@ -356,6 +377,8 @@ extern "C" void fq3_codec_destroy(fq3_codec* c) {
   for (void* p : c->owned) cudaFree(p);
   for (auto* b : c->buf) if (b) cudaFree(b);
   for (auto* b : c->fe.buf) if (b) cudaFree(b);
+  if (c->ext) cudaFree(c->ext);
+  if (c->d_tailptr) { cudaFree(c->d_tailptr); cudaFree(c->d_pos0); cudaFree(c->d_valid); }
   delete c;
 }
 
@@ -498,12 +521,13 @@ extern "C" int fq3_codec_load_weights(fq3_codec* c, const fq3_tensor* tensors, i
 }
 
 static int launch_conv(fq3_codec* c, const Layer& L, const __nv_bfloat16* X, const __nv_bfloat16* R, __nv_bfloat16* Yraw,
-                       __nv_bfloat16* Yact, int T, int batch, cudaStream_t stream) {
+                       __nv_bfloat16* Yact, int T, int batch, cudaStream_t stream, int x_row0 = 0, int x_rows = 0) {
   ConvArgs a;
   a.X = X; a.W = L.W; a.bias = L.bias; a.R = R; a.Yraw = Yraw; a.Yact = Yact; a.ea = L.ea; a.ib = L.ib;
   a.T = T; a.Cin = L.Cin; a.N = L.N; a.taps = L.taps; a.dil = L.dil; a.bias_mod = L.bias_mod; a.act_mod = L.act_mod;
   a.mode = 0;
   a.scale = nullptr; a.scale_mod = 1;
+  a.x_row0 = x_row0; a.x_rows = x_rows;
   a.batch = batch;
   c->launches++;
   if (g_fq3_gemm_backend != 1) {
@@ -567,7 +591,7 @@ static int stack_run(fq3_codec* c, const __nv_bfloat16* xcl, int batch, int T4, 
     cur = a1;
   }
   __nv_bfloat16* act = cur;
-  conv_out_kernel<<<dim3((T + 255) / 256, batch), 256, 0, stream>>>(act, c->w_out, c->b_out, T, c->c_out, 7, pcm_out_dev);
+  conv_out_kernel<<<dim3((T + 255) / 256, batch), 256, 0, stream>>>(act, c->w_out, c->b_out, T, c->c_out, 7, pcm_out_dev, 0, T);
   c->launches++;
   CCK(cudaGetLastError());
   return 0;
@@ -779,12 +803,12 @@ extern "C" int fq3_codec_decode_codes(fq3_codec* c, const int64_t* codes_dev, in
     if ((rc = fe_gemm(c, Cn, y.qkv, nullptr, nullptr, nullptr, D, R0, H, 3 * H, 1, 0, stream))) return rc;
     {
       const long long warps = (long long)R0 * f.nh * 2;
-      fe::rope_qk_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, stream>>>(D, R0, T, f.nh, hd, f.inv_freq);
+      fe::rope_qk_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, stream>>>(D, R0, T, f.nh, hd, f.inv_freq, nullptr);
     }
     {
       dim3 g((T + 7) / 8, f.nh, batch);
-      if (hd == 64) fe::swa_kernel<64><<<g, 256, swa_smem, stream>>>(D, T, f.nh, f.window, E);
-      else fe::swa_kernel<128><<<g, 256, swa_smem, stream>>>(D, T, f.nh, f.window, E);
+      if (hd == 64) fe::swa_kernel<64><<<g, 256, swa_smem, stream>>>(D, T, f.nh, f.window, E, T, 0, nullptr);
+      else fe::swa_kernel<128><<<g, 256, swa_smem, stream>>>(D, T, f.nh, f.window, E, T, 0, nullptr);
     }
     if ((rc = fe_gemm(c, E, y.o, nullptr, y.s1, A, Bx, R0, H, H, 1, 0, stream))) return rc;
     fe::rmsnorm_rows_kernel<<<R0, 256, 0, stream>>>(Bx, y.ln2, H, f.eps, Cn);
@@ -803,7 +827,7 @@ extern "C" int fq3_codec_decode_codes(fq3_codec* c, const int64_t* codes_dev, in
     if ((rc = fe_gemm(c, cur, y.ct, y.ct_b, nullptr, nullptr, A, rows, H, y.r * H, H, 0, stream))) return rc;
     rows *= y.r;
     Tc *= y.r;
-    fe::dwconv_ln_kernel<<<rows, 256, 0, stream>>>(A, Tc, H, y.dw_w, y.dw_b, y.ln_w, y.ln_b, 1e-6f, Bx);
+    fe::dwconv_ln_kernel<<<rows, 256, 0, stream>>>(A, Tc, H, y.dw_w, y.dw_b, y.ln_w, y.ln_b, 1e-6f, Bx, 0, Tc);
     c->launches++;
     if ((rc = fe_gemm(c, Bx, y.pw1, y.pw1_b, nullptr, nullptr, D, rows, H, 4 * H, 4 * H, 2, stream))) return rc;
     if ((rc = fe_gemm(c, D, y.pw2, y.pw2_b, y.gamma, A, out, rows, 4 * H, H, H, 0, stream))) return rc;
@@ -811,6 +835,248 @@ extern "C" int fq3_codec_decode_codes(fq3_codec* c, const int64_t* codes_dev, in
   }
   CCK(cudaGetLastError());
   return stack_run(c, cur, batch, Tc, pcm_out_dev, stream);
+}
+
+
+// ------------------------------------------------------------------------------------------------------------
+// Stateful streaming decode: instead of re-decoding a window of old frames for every chunk
+// (the reference's Phase-1 O(n^2) re-decode and 25-frame Phase-2 context, model.py:1085-1135), every causal layer
+// keeps the tail of its own input -- (k-1)*dilation rows for a causal conv, 1 row for a transposed conv, the last
+// window-1 (k, v) rows for the sliding-window attention -- and a chunk costs only its own frames.  Each output row is
+// computed by exactly the arithmetic of a one-shot decode of the whole sequence (the model is causal), so the PCM of a
+// stream equals the non-streaming decode of the same codes.
+// ------------------------------------------------------------------------------------------------------------
+static __global__ void ext_build_kernel(const __nv_bfloat16* const* __restrict__ tails, size_t off,
+                                        const __nv_bfloat16* __restrict__ X, int h, int T, int C8,
+                                        __nv_bfloat16* __restrict__ E) {
+  // E[b][r][:] = r < h ? tail_b[r][:] : X[b][r - h][:]        (16-byte vectors; C8 = C / 8)
+  const int b = blockIdx.y;
+  const long long n = (long long)(h + T) * C8;
+  const uint4* tb = reinterpret_cast<const uint4*>(tails[b] + off);
+  const uint4* xb = reinterpret_cast<const uint4*>(X) + (size_t)b * T * C8;
+  uint4* eb = reinterpret_cast<uint4*>(E) + (size_t)b * (h + T) * C8;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / C8;
+    eb[i] = r < h ? tb[i] : xb[i - (long long)h * C8];
+  }
+}
+static __global__ void tail_save_kernel(__nv_bfloat16* const* __restrict__ tails, size_t off,
+                                        const __nv_bfloat16* __restrict__ E, int h, int T, int C8) {
+  // tail_b <- last h rows of E[b]
+  const int b = blockIdx.y;
+  const long long n = (long long)h * C8;
+  uint4* tb = reinterpret_cast<uint4*>(tails[b] + off);
+  const uint4* eb = reinterpret_cast<const uint4*>(E) + ((size_t)b * (h + T) + T) * C8;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) tb[i] = eb[i];
+}
+
+static int stream_sites(fq3_codec* c) {
+  if (!c->sites.empty()) return 0;
+  const FrontEnd& f = c->fe;
+  size_t off = 0;
+  auto add = [&](int h, int C) { c->sites.push_back({h, C, off}); off += (size_t)h * C; };
+  for (int l = 0; l < f.L; ++l) add(f.window - 1, 3 * f.H);
+  for (size_t u = 0; u < f.ups.size(); ++u) add(6, f.H);
+  for (const Layer& L : c->layers) add((L.taps - 1) * L.dil, L.Cin);   // pointwise layers: h = 0
+  add(6, c->c_out);
+  c->tail_elems = off;
+  return 0;
+}
+
+extern "C" int fq3_codec_stream_create(fq3_codec* c, fq3_codec_stream** out) {
+  if (!c || !out) return cfail(FQ3_ERR_INVALID, "null argument");
+  if (c->layers.empty() || !c->fe.ready) return cfail(FQ3_ERR_STATE, "codec weights / front end not loaded");
+  CCK(cudaSetDevice(c->dev));
+  stream_sites(c);
+  fq3_codec_stream* s = new fq3_codec_stream();
+  s->owner = c;
+  if (cudaMalloc(&s->tails, c->tail_elems * 2) != cudaSuccess) { delete s; return cfail(FQ3_ERR_CUDA, "cudaMalloc of the stream state failed"); }
+  if (cudaMemset(s->tails, 0, c->tail_elems * 2) != cudaSuccess) { cudaFree(s->tails); delete s; return cfail(FQ3_ERR_CUDA, "cudaMemset failed"); }
+  *out = s;
+  return 0;
+}
+extern "C" int fq3_codec_stream_reset(fq3_codec_stream* s, void* stream_) {
+  if (!s) return cfail(FQ3_ERR_INVALID, "null argument");
+  CCK(cudaSetDevice(s->owner->dev));
+  CCK(cudaMemsetAsync(s->tails, 0, s->owner->tail_elems * 2, (cudaStream_t)stream_));
+  s->frames = 0;
+  return 0;
+}
+extern "C" void fq3_codec_stream_destroy(fq3_codec_stream* s) {
+  if (!s) return;
+  cudaSetDevice(s->owner->dev);
+  cudaFree(s->tails);
+  delete s;
+}
+extern "C" int64_t fq3_codec_stream_frames(fq3_codec_stream* s) { return s ? s->frames : 0; }
+
+/* The next T code frames of n_streams streams (each with its own history) in one set of launches:
+ * codes_dev int64 [n_streams][T][Q] -> pcm float32 [n_streams][T * total_upsample]; pcm_out_dev may be NULL (state
+ * warm-up, e.g. the ICL reference frames: the waveform of the last stage is skipped, every state is updated). */
+extern "C" int fq3_codec_stream_decode(fq3_codec* c, fq3_codec_stream* const* streams, int32_t n_streams,
+                                       const int64_t* codes_dev, int32_t T, float* pcm_out_dev, void* stream_) {
+  if (!c || !streams || !codes_dev || T <= 0 || n_streams <= 0) return cfail(FQ3_ERR_INVALID, "null argument");
+  FrontEnd& f = c->fe;
+  if (c->layers.empty() || !f.ready) return cfail(FQ3_ERR_STATE, "codec weights / front end not loaded");
+  for (int b = 0; b < n_streams; ++b) {
+    if (!streams[b] || streams[b]->owner != c) return cfail(FQ3_ERR_INVALID, "stream does not belong to this codec");
+    for (int a = 0; a < b; ++a)
+      if (streams[a] == streams[b]) return cfail(FQ3_ERR_INVALID, "stream listed twice");
+  }
+  CCK(cudaSetDevice(c->dev));
+  cudaStream_t stream = (cudaStream_t)stream_;
+  stream_sites(c);
+  const int batch = n_streams;
+  const int H = f.H, I = f.I, hd = H / f.nh, W1 = f.window - 1;
+  // ---- per-call stream tables
+  if (batch > c->tab_cap) {
+    if (c->d_tailptr) { cudaFree(c->d_tailptr); cudaFree(c->d_pos0); cudaFree(c->d_valid); }
+    CCK(cudaMalloc(&c->d_tailptr, batch * sizeof(void*)));
+    CCK(cudaMalloc(&c->d_pos0, batch * sizeof(int)));
+    CCK(cudaMalloc(&c->d_valid, batch * sizeof(int)));
+    c->tab_cap = batch;
+  }
+  {
+    std::vector<void*> tp(batch);
+    std::vector<int> p0(batch), vd(batch);
+    for (int b = 0; b < batch; ++b) {
+      tp[b] = streams[b]->tails;
+      p0[b] = (int)streams[b]->frames;
+      vd[b] = (int)std::min<long long>(streams[b]->frames, W1);
+    }
+    CCK(cudaMemcpyAsync(c->d_tailptr, tp.data(), batch * sizeof(void*), cudaMemcpyHostToDevice, stream));
+    CCK(cudaMemcpyAsync(c->d_pos0, p0.data(), batch * sizeof(int), cudaMemcpyHostToDevice, stream));
+    CCK(cudaMemcpyAsync(c->d_valid, vd.data(), batch * sizeof(int), cudaMemcpyHostToDevice, stream));
+    // pageable sources: cudaMemcpyAsync returns once they have been staged, so the vectors may go out of scope here
+  }
+  // ---- buffers
+  const size_t rows0 = (size_t)batch * T;
+  size_t up = 1;
+  for (auto& u : f.ups) up *= (size_t)u.r;
+  const size_t rowsU = rows0 * up;
+  if (rowsU > f.cap_rows) {
+    for (auto*& b : f.buf) { if (b) cudaFree(b); b = nullptr; }
+    const size_t wide = std::max(rows0 * (size_t)std::max(3 * H, I), rowsU * (size_t)4 * H);
+    for (int i = 0; i < 5; ++i) CCK(cudaMalloc(&f.buf[i], (i == 3 ? wide : rowsU * (size_t)H) * 2));
+    f.cap_rows = rowsU;
+  }
+  int rc;
+  if ((rc = stack_reserve(c, batch, (int)(T * up)))) return rc;
+  {
+    size_t need = 0, Tl = T;
+    size_t si = 0;
+    for (int l = 0; l < f.L; ++l, ++si) need = std::max(need, (size_t)(c->sites[si].h + Tl) * c->sites[si].C);
+    for (auto& u : f.ups) { Tl *= u.r; need = std::max(need, (size_t)(c->sites[si].h + Tl) * c->sites[si].C); ++si; }
+    for (const Layer& L : c->layers) { need = std::max(need, (size_t)(c->sites[si].h + Tl) * c->sites[si].C); ++si; Tl *= L.upsample; }
+    need = std::max(need, (size_t)(c->sites[si].h + Tl) * c->sites[si].C);
+    need *= (size_t)batch;
+    if (need > c->ext_cap) {
+      if (c->ext) cudaFree(c->ext);
+      c->ext = nullptr;
+      CCK(cudaMalloc(&c->ext, need * 2));
+      c->ext_cap = need;
+    }
+  }
+  size_t site = 0;
+  // history rows of site `site` in front of the new rows X [batch][Tn][C]  ->  c->ext [batch][h + Tn][C]; state updated
+  auto with_history = [&](const __nv_bfloat16* X, int Tn) -> const __nv_bfloat16* {
+    const fq3_codec::Site& st = c->sites[site++];
+    if (st.h == 0) return X;
+    const int C8 = st.C / 8;
+    const long long n = (long long)(st.h + Tn) * C8;
+    dim3 g((unsigned)std::min<long long>((n + 255) / 256, 1024), batch);
+    ext_build_kernel<<<g, 256, 0, stream>>>((const __nv_bfloat16* const*)c->d_tailptr, st.off, X, st.h, Tn, C8, c->ext);
+    dim3 g2((unsigned)std::min<long long>(((long long)st.h * C8 + 255) / 256, 256), batch);
+    tail_save_kernel<<<g2, 256, 0, stream>>>((__nv_bfloat16* const*)c->d_tailptr, st.off, c->ext, st.h, Tn, C8);
+    c->launches += 2;
+    return c->ext;
+  };
+  auto hist = [&](size_t i) { return c->sites[i].h; };
+  // ---- front end
+  __nv_bfloat16 *A = f.buf[0], *Bx = f.buf[1], *Cn = f.buf[2], *D = f.buf[3], *E = f.buf[4];
+  const int R0 = (int)rows0;
+  fe::embed_mean_kernel<<<R0, 256, 0, stream>>>((const long long*)codes_dev, f.emb, f.Q, f.codebook, H, A);
+  c->launches++;
+  const int Wpad = (f.window + 31) & ~31;
+  const size_t swa_smem = (size_t)(8 * Wpad + 8 * hd) * sizeof(float);
+  for (int l = 0; l < f.L; ++l) {
+    const FeLayer& y = f.layers[l];
+    fe::rmsnorm_rows_kernel<<<R0, 256, 0, stream>>>(A, y.ln1, H, f.eps, Cn);
+    if ((rc = fe_gemm(c, Cn, y.qkv, nullptr, nullptr, nullptr, D, R0, H, 3 * H, 1, 0, stream))) return rc;
+    {
+      const long long warps = (long long)R0 * f.nh * 2;
+      fe::rope_qk_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, stream>>>(D, R0, T, f.nh, hd, f.inv_freq, c->d_pos0);
+    }
+    const int h = hist(site);
+    const __nv_bfloat16* qkv = with_history(D, T);
+    {
+      dim3 g((T + 7) / 8, f.nh, batch);
+      if (hd == 64) fe::swa_kernel<64><<<g, 256, swa_smem, stream>>>(qkv, T, f.nh, f.window, E, h + T, h, c->d_valid);
+      else fe::swa_kernel<128><<<g, 256, swa_smem, stream>>>(qkv, T, f.nh, f.window, E, h + T, h, c->d_valid);
+    }
+    if ((rc = fe_gemm(c, E, y.o, nullptr, y.s1, A, Bx, R0, H, H, 1, 0, stream))) return rc;
+    fe::rmsnorm_rows_kernel<<<R0, 256, 0, stream>>>(Bx, y.ln2, H, f.eps, Cn);
+    if ((rc = fe_gemm(c, Cn, y.gu, nullptr, nullptr, nullptr, D, R0, H, 2 * I, 1, 1, stream))) return rc;
+    if ((rc = fe_gemm(c, D, y.down, nullptr, y.s2, Bx, A, R0, I, H, 1, 0, stream))) return rc;
+    c->launches += 4;
+  }
+  fe::rmsnorm_rows_kernel<<<R0, 256, 0, stream>>>(A, f.norm, H, f.eps, Cn);
+  c->launches++;
+  __nv_bfloat16* cur = Cn;
+  int rows = R0, Tc = T;
+  for (size_t u = 0; u < f.ups.size(); ++u) {
+    const FeUp& y = f.ups[u];
+    __nv_bfloat16* out = (cur == Cn) ? E : Cn;
+    if ((rc = fe_gemm(c, cur, y.ct, y.ct_b, nullptr, nullptr, A, rows, H, y.r * H, H, 0, stream))) return rc;
+    rows *= y.r;
+    Tc *= y.r;
+    const int h = hist(site);
+    const __nv_bfloat16* xin = with_history(A, Tc);
+    fe::dwconv_ln_kernel<<<rows, 256, 0, stream>>>(xin, Tc, H, y.dw_w, y.dw_b, y.ln_w, y.ln_b, 1e-6f, Bx, h, h + Tc);
+    c->launches++;
+    if ((rc = fe_gemm(c, Bx, y.pw1, y.pw1_b, nullptr, nullptr, D, rows, H, 4 * H, 4 * H, 2, stream))) return rc;
+    if ((rc = fe_gemm(c, D, y.pw2, y.pw2_b, y.gamma, A, out, rows, 4 * H, H, H, 0, stream))) return rc;
+    cur = out;
+  }
+  // ---- waveform stack (stack_run with the history detours)
+  int Ts = Tc;
+  size_t li = 0;
+  auto conv = [&](const Layer& L, const __nv_bfloat16* X, const __nv_bfloat16* R, __nv_bfloat16* Yraw, __nv_bfloat16* Yact) -> int {
+    const int h = hist(site);
+    const __nv_bfloat16* xin = with_history(X, Ts);
+    return launch_conv(c, L, xin, R, Yraw, Yact, Ts, batch, stream, h, h + Ts);
+  };
+  __nv_bfloat16* act = c->buf[1];
+  if ((rc = conv(c->layers[li++], cur, nullptr, nullptr, act))) return rc;
+  for (int bi = 0; bi < c->n_blocks; ++bi) {
+    __nv_bfloat16* fr[3];
+    int k = 0;
+    for (auto* b : c->buf)
+      if (b != act) fr[k++] = b;
+    __nv_bfloat16 *x = fr[0], *a1 = fr[1], *a2 = fr[2], *y = act;
+    const Layer& U = c->layers[li++];
+    if ((rc = conv(U, act, nullptr, x, a1))) return rc;
+    Ts *= U.upsample;
+    for (int j = 0; j < 3; ++j) {
+      const Layer& C1 = c->layers[li++];
+      const Layer& C2 = c->layers[li++];
+      if ((rc = conv(C1, a1, nullptr, nullptr, a2))) return rc;
+      if ((rc = conv(C2, a2, x, C2.write_raw ? y : nullptr, a1))) return rc;
+      std::swap(x, y);
+    }
+    act = a1;
+  }
+  {
+    const int h = hist(site);
+    const __nv_bfloat16* xin = with_history(act, Ts);
+    if (pcm_out_dev) {
+      conv_out_kernel<<<dim3((Ts + 255) / 256, batch), 256, 0, stream>>>(xin, c->w_out, c->b_out, Ts, c->c_out, 7, pcm_out_dev, h, h + Ts);
+      c->launches++;
+    }
+  }
+  CCK(cudaGetLastError());
+  for (int b = 0; b < batch; ++b) streams[b]->frames += T;
+  return 0;
 }
 
 extern "C" int fq3_codec_decode(fq3_codec* c, const void* x_dev, int32_t T4, float* pcm_out_dev, void* stream_) {

@@ -110,8 +110,6 @@ struct KParams {
   float* PART;                 // [nH][attn_split][PART_STRIDE] partial attention results (acc[128], max, sum)
   unsigned* attn_cnt;          // [nH] arrival counters of the splits (cleared with the barrier words every launch)
   int mma_tape;                // 1: bf16 tensor-core fragment layout, 0: fp32 row-chunk layout
-  int l2_lead;                 // bytes of this CTA's tape slice the producer keeps requested into L2 AHEAD of its TMA loads
-                               // (cp.async.bulk.prefetch.L2) while the ring is full; 0 = off
   // ---- batched decode (fq3_decode_batch.cuh): B request slots share one pass over the weight tape
   int nslots;                  // columns of this launch (0: single-sequence kernel)
   const SlotParams* sl;        // [nslots] per-column request state (device)
@@ -497,31 +495,6 @@ struct Producer {
   uint32_t ctr;
   bool stopped;
   uint64_t pol_first, pol_last;  // L2 eviction policies: stream-once weights vs weights re-read 15x per frame
-  // ---- L2 run-ahead: this CTA's slice of a stack (all layers, + the talker head) is ONE contiguous tape range consumed
-  // front to back.  While the ring is full (consumers sit in a barrier / attention) the producer keeps asking L2 for the
-  // bytes behind the last issued tile, up to `l2_lead` ahead, so HBM keeps streaming across the phases in which nothing
-  // is consumed and the ring refills from L2 afterwards.
-  const uint8_t* pf_ptr = nullptr;
-  const uint8_t* pf_end = nullptr;
-  __device__ __forceinline__ void pf_range(int seg_first, int seg_last) {   // contiguous slice [first seg, last seg]
-    pf_ptr = pf_end = nullptr;
-    if (P.l2_lead <= 0) return;
-    const uint32_t a = s.seg[seg_first], b = s.seg[seg_last];
-    if ((a & 255u) == 0u || (b & 255u) == 0u) return;
-    const Grp g0 = s.grp[a >> 8], g1 = s.grp[(b >> 8) + (b & 255u) - 1];
-    const uint32_t tb = P.mma_tape ? (uint32_t)(g1.rows & 0xff) * g1.m * 2048u : (uint32_t)g1.rows * g1.m * 512u;
-    pf_ptr = P.tape + (size_t)g0.off16 * 16;
-    pf_end = P.tape + (size_t)g1.off16 * 16 + (size_t)tb * g1.ntiles;
-  }
-  __device__ __forceinline__ void pf_step(const uint8_t* next_load) {
-    if (pf_ptr == nullptr) return;
-    if (pf_ptr < next_load) pf_ptr = next_load;
-    if (pf_ptr < pf_end && pf_ptr < next_load + P.l2_lead) {
-      const uint32_t n = (uint32_t)min((long long)STAGE_BYTES, (long long)(pf_end - pf_ptr));
-      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(pf_ptr), "r"(n) : "memory");
-      pf_ptr += n;
-    }
-  }
   __device__ __forceinline__ void seg(int sg, bool keep = false) {
     if (stopped) return;
     const uint32_t st = s.seg[sg];
@@ -539,11 +512,6 @@ struct Producer {
             stopped = true;
             return;
           }
-          pf_step(src + (size_t)tl * bytes);
-        }
-        if (flag_ld(&s.stop_flag)) {
-          stopped = true;
-          return;
         }
         mbar_expect_tx(&s.full[stage], bytes);
         bulk_g2s_hint(s.ring[stage], src + (size_t)tl * bytes, bytes, &s.full[stage], keep ? pol_last : pol_first);
@@ -572,10 +540,6 @@ struct Producer {
           return;
         }
       }
-      if (flag_ld(&s.stop_flag)) {
-        stopped = true;
-        return;
-      }
       mbar_expect_tx(&s.full[stage], 2 * bytes);
       bulk_g2s(s.ring[stage], kb + (size_t)tl * KVT_KEYS * 256, bytes, &s.full[stage]);
       bulk_g2s(s.ring[stage] + KVT_VOFF, vb + (size_t)tl * KVT_KEYS * 256, bytes, &s.full[stage]);
@@ -583,9 +547,7 @@ struct Producer {
     }
   }
   // kv_slot0 >= 0: talker step at cache slot kv_slot0 with split attention
-  __device__ __forceinline__ void stack_layers(const StackDev& S, int keep_layers = 0, int kv_slot0 = -1, int kv_start = 0,
-                                               bool with_head = false) {
-    pf_range(S.seg_base, with_head ? S.seg_head : S.seg_base + 4 * S.L - 1);
+  __device__ __forceinline__ void stack_layers(const StackDev& S, int keep_layers = 0, int kv_slot0 = -1, int kv_start = 0) {
     for (int l = 0; l < S.L; ++l)
       for (int q = 0; q < 4; ++q) {
         seg(S.seg_base + 4 * l + q, l < keep_layers);
@@ -1841,7 +1803,7 @@ __device__ __noinline__ void producer_main(const KParams& P) {
             pr.seg(P.p.seg_head + i);
           }
           if (P.mode == MODE_FUSED) {
-            pr.stack_layers(P.t, 0, P.prefill_len + P.state[1] + f, P.n_left_pad, true);
+            pr.stack_layers(P.t, 0, P.prefill_len + P.state[1] + f, P.n_left_pad);
             pr.seg(P.t.seg_head);
           }
         }

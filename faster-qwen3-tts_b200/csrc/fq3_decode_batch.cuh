@@ -863,14 +863,10 @@ __device__ __noinline__ void producer_batch_main(const KParams& P) {
     for (int f = 0; P.mode != MODE_GEMV_TEST && f < P.n_frames && !pr.stopped; ++f) {
       if (P.has_mtp) rep(P.seg_mtp, nb2, true);
       for (int i = 0; i < P.ncb; ++i) {
-        if ((i == 0 ? nb2 : nb1) == 1) pr.pf_range(P.p.seg_base, P.p.seg_base + 4 * P.p.L - 1);
-        else pr.pf_ptr = nullptr;   // replayed segments: no run-ahead
         for (int l = 0; l < P.p.L; ++l)
           for (int q = 0; q < 4; ++q) rep(P.p.seg_base + 4 * l + q, i == 0 ? nb2 : nb1, l < P.pred_pin_layers);
         rep(P.p.seg_head + i, nb1, false);
       }
-      if (nb1 == 1) pr.pf_range(P.t.seg_base, P.t.seg_head);
-      else pr.pf_ptr = nullptr;
       for (int l = 0; l < P.t.L; ++l)
         for (int q = 0; q < 4; ++q) rep(P.t.seg_base + 4 * l + q, nb1, false);
       rep(P.t.seg_head, nb1, false);

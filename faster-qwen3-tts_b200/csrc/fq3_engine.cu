@@ -367,8 +367,6 @@ extern "C" int fq3_engine_create(const fq3_config* cfg, fq3_engine** out) {
   k.dbg = e->dbg; k.dbg_stride_layer = e->dbg_stride;
   k.pred_pin_layers = 2;
   if (const char* v = getenv("FQ3_PRED_PIN")) k.pred_pin_layers = std::max(atoi(v), 0);   // tuning knob
-  k.l2_lead = 0;
-  if (const char* v = getenv("FQ3_L2_LEAD_KB")) k.l2_lead = std::max(atoi(v), 0) * 1024;     // producer L2 run-ahead per CTA
   {
     // split-key talker attention (bf16 engines): S CTAs per q-head; a slice must fit the 4 ring tiles it may hold
     int Sx = e->bf16 ? std::min(e->ncta / std::max(T.num_attention_heads, 1), 16) : 0;

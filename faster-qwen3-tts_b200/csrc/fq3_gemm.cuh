@@ -30,6 +30,9 @@ struct ConvArgs {
   int mode;                 // 0 general, 1 SwiGLU pair epilogue (Yraw is [T][N/2]), 2 general with GELU
   const float* scale;       // per-column factor [scale_mod] applied to rnd(acc + bias) before the residual, or null
   int scale_mod;
+  // stateful streaming (history rows in front of the new ones): X is [batch][x_rows][Cin] and output row m reads input
+  // rows x_row0 + m - shift; rows outside [0, x_rows) read as zero.  x_rows == 0 means x_rows = T, x_row0 = 0.
+  int x_row0, x_rows;
   int batch;                // independent sequences: X is [batch][T][Cin], R / Yraw / Yact are [batch][T][N]; every
                             // sequence has its own causal left padding (0 or 1 = a single sequence)
 };
@@ -71,7 +74,8 @@ static __global__ void __launch_bounds__(CTHREADS, 2) conv_gemm_kernel(  // stat
   const int m0 = (blockIdx.x - bidx * tiles_m) * BM, n0 = blockIdx.y * BN;
   const int kc = a.Cin / BK;                 // k-steps per tap
   const int nks = a.taps * kc;
-  const __nv_bfloat16* Xb = a.X + (size_t)bidx * a.T * a.Cin;
+  const int xrows = a.x_rows > 0 ? a.x_rows : a.T;
+  const __nv_bfloat16* Xb = a.X + (size_t)bidx * xrows * a.Cin;
   const size_t ybase = (size_t)bidx * a.T * a.N;
 
   auto load_stage = [&](int ks, int stage) {
@@ -83,8 +87,8 @@ static __global__ void __launch_bounds__(CTHREADS, 2) conv_gemm_kernel(  // stat
     for (int i = 0; i < 2; ++i) {  // 128 rows x 4 chunks
       const int q = tid + i * CTHREADS;
       const int row = q >> 2, ch = q & 3;
-      const int t = m0 + row - shift;
-      const bool ok = t >= 0 && t < a.T && (m0 + row) < a.T;
+      const int t = m0 + row - shift + a.x_row0;
+      const bool ok = t >= 0 && t < xrows && (m0 + row) < a.T;
       const __nv_bfloat16* src = Xb + ((size_t)(ok ? t : 0) * a.Cin + c0 + ch * 8);
       cp_async16(A + swz(row, ch), src, ok);
     }

@@ -208,7 +208,7 @@ static __global__ void __launch_bounds__(TTHREADS, DEEP ? 1 : 2)
         uint8_t* A = tiles + s * C::STAGE;
         uint8_t* B = A + C::A_BYTES;
         mb_expect(&full[s], C::STAGE);
-        tma_load_3d(A, &tmX, c0, m0 - shift, bidx, &full[s]);    // rows < 0 or >= T of this sequence are zero-filled by TMA
+        tma_load_3d(A, &tmX, c0, m0 - shift + a.x_row0, bidx, &full[s]);    // rows < 0 or >= T of this sequence are zero-filled by TMA
         tma_load_2d(B, &tmW, tap * a.Cin + c0, n0, &full[s]);
       }
     }
@@ -262,7 +262,10 @@ static __global__ void __launch_bounds__(TTHREADS, DEEP ? 1 : 2)
 
 
 // ------------------------------------------------------------------------------------------------------------
-// Persistent variant: one CTA per SM walks a strided list of output tiles; the fp32 accumulator is DOUBLE-BUFFERED in
+// Persistent variant (A/B only -- measured 3-15 % SLOWER than the one-tile-per-CTA kernel on the codec shapes: with one
+// CTA per SM a single TMA thread and a single MMA thread issue every k-step of ~50 ns, whereas 2-4 co-resident one-tile
+// CTAs give the SM several independent issue chains and overlap each other's prologue / epilogue anyway):
+// one CTA per SM walks a strided list of output tiles; the fp32 accumulator is DOUBLE-BUFFERED in
 // TMEM (2 x 128 columns), so the epilogue of tile i (tcgen05.ld -> bias / residual / SnakeBeta -> stores) runs while
 // the TMA / MMA warps are already in the main loop of tile i+1; barriers, TMEM and the descriptor prefetch are paid
 // once per CTA instead of once per tile, and the smem ring never drains between tiles.  Tile order: M fastest, so the
@@ -326,7 +329,7 @@ static __global__ void __launch_bounds__(TTHREADS, 1)
           const int shift = (a.taps - 1 - tap) * a.dil;
           uint8_t* A = tiles + s * C::STAGE;
           mb_expect(&full[s], C::STAGE);
-          tma_load_3d(A, &tmX, c0, m0 - shift, bidx, &full[s]);
+          tma_load_3d(A, &tmX, c0, m0 - shift + a.x_row0, bidx, &full[s]);
           tma_load_2d(A + C::A_BYTES, &tmW, tap * a.Cin + c0, n0, &full[s]);
         }
       }
@@ -472,7 +475,8 @@ static bool cached_map(CUtensorMap* tm, const void* base, uint64_t batch /*0: 2-
 }
 
 // returns 0 on success, 1 if this shape must use the mma.sync fallback, <0 on CUDA error
-// variant: 0 = persistent kernel when a CTA would get more than one tile (default), 2 = always one tile per CTA
+// variant: 0 = one tile per CTA, 2-4 CTAs co-resident per SM (default: measured faster, profiles/r2c_codec_gemm_variants.jsonl),
+//          2 = persistent kernel (double-buffered TMEM accumulator) whenever a CTA would get more than one tile
 static int launch_tc(const fq3gemm::ConvArgs& a, cudaStream_t stream, int variant = 0) {
   static bool attr_done = false;
   static int num_sms = 148;
@@ -494,11 +498,11 @@ static int launch_tc(const fq3gemm::ConvArgs& a, cudaStream_t stream, int varian
   if (a.mode == 1 ? (a.N % 32 != 0) : (a.N % 8 != 0)) return 1;
   CUtensorMap tmX, tmW;
   const int nb = a.batch > 1 ? a.batch : 1;
-  if (!cached_map(&tmX, a.X, (uint64_t)nb, (uint64_t)a.T, (uint64_t)a.Cin, TBM, BK)) return 1;
+  if (!cached_map(&tmX, a.X, (uint64_t)nb, (uint64_t)(a.x_rows > 0 ? a.x_rows : a.T), (uint64_t)a.Cin, TBM, BK)) return 1;
   if (!cached_map(&tmW, a.W, 0, (uint64_t)a.N, (uint64_t)a.taps * a.Cin, TBN, BK)) return 1;
   dim3 grid(((a.T + TBM - 1) / TBM) * nb, (a.N + TBN - 1) / TBN);
   const long long ntiles = (long long)grid.x * grid.y;
-  if (variant == 0 && ntiles > num_sms && ntiles < (1ll << 30)) {
+  if (variant == 2 && ntiles > num_sms && ntiles < (1ll << 30)) {
     const int tiles_m = (a.T + TBM - 1) / TBM;
     if (BK == 64) conv_gemm_tcp_kernel<64><<<num_sms, TTHREADS, PCfg<64>::SMEM, stream>>>(tmX, tmW, a, tiles_m, tiles_m * nb, (int)ntiles);
     else conv_gemm_tcp_kernel<32><<<num_sms, TTHREADS, PCfg<32>::SMEM, stream>>>(tmX, tmW, a, tiles_m, tiles_m * nb, (int)ntiles);

@@ -411,12 +411,78 @@ class SpeechTokenizer:
         self.launches = int(self._lib.fq3_codec_launch_count(self._h))
         return [pcm[b] for b in range(B)], self.sample_rate
 
+    # ---- stateful streaming (fq3_codec_stream_*) -----------------------------------------------------------
+    def open_stream(self) -> "CodecStream":
+        """A decoder stream that keeps every causal layer's history on the device: ``push(codes[n,16])`` returns the
+        1920*n samples of exactly those frames, at the cost of n frames (no window re-decode)."""
+        if self.backend != "engine" or not self.native_front:
+            raise RuntimeError("stateful streaming needs the engine backend with the native front end")
+        return CodecStream(self)
+
+    @torch.inference_mode()
+    def push_streams(self, streams, codes: torch.Tensor, want_pcm: bool = True):
+        """The next n frames of several streams in ONE set of launches: codes [B, n, 16] -> list of B PCM tensors
+        (or None with want_pcm=False: state warm-up, e.g. the ICL reference frames)."""
+        import ctypes as C
+        codes = codes.to(device=self._dev, dtype=torch.long).contiguous()
+        B, n, Q = codes.shape
+        if B != len(streams):
+            raise ValueError("one row of codes per stream")
+        pcm = torch.empty(B, n * self.decoder.config.total_upsample, dtype=torch.float32, device=self._dev) if want_pcm else None
+        arr = (C.c_void_p * B)(*[s._h for s in streams])
+        with torch.cuda.device(self._dev):
+            rc = self._lib.fq3_codec_stream_decode(self._h, arr, B, C.c_void_p(codes.data_ptr()), n,
+                                                   C.c_void_p(pcm.data_ptr()) if want_pcm else None,
+                                                   C.c_void_p(torch.cuda.current_stream(self._dev).cuda_stream))
+        if rc:
+            raise RuntimeError(self._lib.fq3_codec_last_error().decode())
+        self.launches = int(self._lib.fq3_codec_launch_count(self._h))
+        return [pcm[b] for b in range(B)] if want_pcm else None
+
     def flops(self, T: int) -> float:
         """dense-layer FLOPs of the waveform stack for T code frames"""
         return float(self._lib.fq3_codec_flops(self._h, 4 * T)) if self._h is not None else 0.0
 
     def frontend_flops(self, T: int) -> float:
         return float(self._lib.fq3_codec_frontend_flops(self._h, T)) if self._h is not None else 0.0
+
+
+class CodecStream:
+    """One stateful decoder stream (C ABI fq3_codec_stream_*): history of every causal layer lives on the device."""
+
+    def __init__(self, st: SpeechTokenizer):
+        import ctypes as C
+        self.st = st
+        h = C.c_void_p()
+        with torch.cuda.device(st._dev):
+            if st._lib.fq3_codec_stream_create(st._h, C.byref(h)):
+                raise RuntimeError(st._lib.fq3_codec_last_error().decode())
+        self._h = h
+
+    @property
+    def frames(self) -> int:
+        return int(self.st._lib.fq3_codec_stream_frames(self._h))
+
+    def push(self, codes: torch.Tensor) -> torch.Tensor:
+        """codes [n,16] -> PCM float32 [1920*n] of exactly these frames"""
+        return self.st.push_streams([self], codes.reshape(1, -1, codes.shape[-1]))[0]
+
+    def warm(self, codes: torch.Tensor) -> None:
+        """feed frames whose audio is not wanted (the ICL reference): state only"""
+        self.st.push_streams([self], codes.reshape(1, -1, codes.shape[-1]), want_pcm=False)
+
+    def reset(self) -> None:
+        import ctypes as C
+        with torch.cuda.device(self.st._dev):
+            self.st._lib.fq3_codec_stream_reset(self._h, C.c_void_p(torch.cuda.current_stream(self.st._dev).cuda_stream))
+
+    def __del__(self):
+        try:
+            if self._h is not None and self.st._h is not None:
+                self.st._lib.fq3_codec_stream_destroy(self._h)
+            self._h = None
+        except Exception:
+            pass
 
 
 def build_codec(cfg: Code2WavConfig = None, seed: int = 0, dtype=torch.bfloat16, device="cpu",

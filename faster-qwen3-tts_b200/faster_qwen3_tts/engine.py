@@ -64,7 +64,9 @@ EXPORTS = [
     "fq3_num_ctas", "fq3_launch_count", "fq3_last_error", "fq3_version", "fq3_barrier_test",
     "fq3_engine_set_prefill_weights", "fq3_prefill", "fq3_set_gemm_backend", "fq3_max_batch", "fq3_debug_gemv",
     "fq3_codec_create", "fq3_codec_load_weights", "fq3_codec_decode", "fq3_codec_decode_batch", "fq3_codec_flops",
-    "fq3_codec_load_frontend", "fq3_codec_decode_codes", "fq3_codec_frontend_flops", "fq3_codec_launch_count",
+    "fq3_codec_load_frontend", "fq3_codec_decode_codes", "fq3_codec_frontend_flops",
+    "fq3_codec_stream_create", "fq3_codec_stream_reset", "fq3_codec_stream_destroy", "fq3_codec_stream_frames",
+    "fq3_codec_stream_decode", "fq3_codec_launch_count",
     "fq3_codec_destroy", "fq3_codec_last_error",
 ]
 
@@ -137,6 +139,14 @@ def load_library() -> C.CDLL:
     lib.fq3_codec_load_frontend.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_float), C.c_int32,
                                             C.POINTER(Tensor), C.c_int32, C.c_void_p]
     lib.fq3_codec_decode_codes.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
+    lib.fq3_codec_stream_create.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+    lib.fq3_codec_stream_reset.argtypes = [C.c_void_p, C.c_void_p]
+    lib.fq3_codec_stream_destroy.argtypes = [C.c_void_p]
+    lib.fq3_codec_stream_destroy.restype = None
+    lib.fq3_codec_stream_frames.argtypes = [C.c_void_p]
+    lib.fq3_codec_stream_frames.restype = C.c_int64
+    lib.fq3_codec_stream_decode.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_int32, C.c_void_p, C.c_int32, C.c_void_p,
+                                            C.c_void_p]
     lib.fq3_codec_frontend_flops.argtypes = [C.c_void_p, C.c_int32]
     lib.fq3_codec_frontend_flops.restype = C.c_double
     lib.fq3_codec_flops.argtypes = [C.c_void_p, C.c_int32]
@@ -149,10 +159,10 @@ def load_library() -> C.CDLL:
 
 
 def set_gemm_backend(name: str):
-    """Dense layers of K3 (prefill) and K4 (codec): 'tcgen05' (default: persistent tile loop with a double-buffered TMEM
-    accumulator whenever a CTA gets more than one tile), 'tcgen05_1tile' (one tile per CTA, the round-1 kernel) or 'mma'
+    """Dense layers of K3 (prefill) and K4 (codec): 'tcgen05' (default: one 128x96 tile per CTA, 2-4 CTAs per SM),
+    'tcgen05_persistent' (tile loop with a double-buffered TMEM accumulator; measured slower on these shapes) or 'mma'
     (mma.sync kernel) -- the last two for A/B runs."""
-    load_library().fq3_set_gemm_backend({"tcgen05": 0, "mma": 1, "tcgen05_1tile": 2}[name])
+    load_library().fq3_set_gemm_backend({"tcgen05": 0, "mma": 1, "tcgen05_persistent": 2}[name])
 
 
 class EngineError(RuntimeError):

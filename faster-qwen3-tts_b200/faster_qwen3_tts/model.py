@@ -16,6 +16,7 @@ the synthetic model (``from_synthetic``) answers them with deterministic stand-i
 from __future__ import annotations
 
 import logging
+import os
 import time
 from pathlib import Path
 from typing import Any, Dict, Generator, List, Optional, Tuple, Union
@@ -77,9 +78,38 @@ class _StreamWindow:
         return self.finish(audio_list[0], meta), sr
 
 
+class _StatefulWindow:
+    """Streaming decode on a stateful codec stream (``streaming_codec="stateful"``): every chunk costs
+    only its own frames -- no Phase-1 re-decode of everything so far, no 25-frame Phase-2 context (model.py:1085-1135).
+    The audio of a request equals the non-streaming decode of the same codes (``generate_voice_clone``), i.e. the
+    reference's Phase-1 output continued for the whole utterance; Phase-2 chunks of the reference differ slightly because
+    they see only 25 frames of context.  ICL reference frames warm the stream's state up front; no audio is made for them."""
+
+    def __init__(self, owner, speech_tokenizer, ref_codes, chunk_size, to_host=True):
+        self.st = speech_tokenizer
+        self.stream = speech_tokenizer.open_stream()
+        self.conv = owner._to_numpy if to_host else (lambda a: a.flatten())
+        if ref_codes is not None and ref_codes.shape[0] > 0:
+            self.stream.warm(ref_codes)
+
+    def push(self, codec_chunk):
+        return self.conv(self.stream.push(codec_chunk)), self.st.sample_rate
+
+
 def decode_windows_batched(speech_tokenizer, wins, chunks):
     """One chunk of several requests: windows of equal length are decoded as ONE batch (every codec launch covers all of
     them); returns [(new_audio, sample_rate)] in the order of `wins`."""
+    if wins and isinstance(wins[0], _StatefulWindow):
+        # stateful streams: rows with the same number of new frames advance together in one set of launches
+        groups = {}
+        for i, c in enumerate(chunks):
+            groups.setdefault(int(c.shape[0]), []).append(i)
+        out = [None] * len(wins)
+        for n, idxs in groups.items():
+            pcm = speech_tokenizer.push_streams([wins[i].stream for i in idxs], torch.stack([chunks[i] for i in idxs]))
+            for i, a in zip(idxs, pcm):
+                out[i] = (wins[i].conv(a), speech_tokenizer.sample_rate)
+        return out
     prepared = [w.window(c) for w, c in zip(wins, chunks)]
     groups = {}
     for i, (codes, _) in enumerate(prepared):
@@ -105,6 +135,9 @@ class FasterQwen3TTS:
         self.sample_rate = self._infer_sample_rate(base_model)
         self._warmed_up = False
         self._voice_prompt_cache = {}
+        # "window": the reference's two-phase re-decode policy (sample-exact, default); "stateful": one stateful decoder
+        # stream per request (engine codec only) -- each chunk costs its own frames, audio = the non-streaming decode
+        self.streaming_codec = os.environ.get("FQ3_STREAMING_CODEC", "window")
 
     # ------------------------------------------------------------------ small surface kept from the reference
     @staticmethod
@@ -421,10 +454,17 @@ class FasterQwen3TTS:
         """The reference's hybrid streaming decode (model.py:1052-1135): Phase 1 re-decodes everything so far
         (reference codes prepended in ICL mode) until max(25, chunk_size) frames exist and calibrates
         samples_per_frame; Phase 2 decodes a 25-frame left-context window and trims the context."""
-        win = _StreamWindow(self, speech_tokenizer, ref_codes, chunk_size, to_host)
+        win = self._make_window(speech_tokenizer, ref_codes, chunk_size, to_host)
         for codec_chunk, timing in chunks:
             new_audio, sr = win.push(codec_chunk)
             yield new_audio, sr, timing
+
+    def _make_window(self, speech_tokenizer, ref_codes, chunk_size, to_host=True):
+        if self.streaming_codec == "stateful" and hasattr(speech_tokenizer, "open_stream"):
+            return _StatefulWindow(self, speech_tokenizer, ref_codes, chunk_size, to_host)
+        if self.streaming_codec not in ("window", "stateful"):
+            raise ValueError("streaming_codec must be 'window' or 'stateful'")
+        return _StreamWindow(self, speech_tokenizer, ref_codes, chunk_size, to_host)
 
     def _gen_kwargs(self, max_new_tokens, min_new_tokens, temperature, top_k, top_p, do_sample, repetition_penalty):
         return dict(max_new_tokens=max_new_tokens, min_new_tokens=min_new_tokens, temperature=temperature, top_k=top_k,
@@ -468,7 +508,7 @@ class FasterQwen3TTS:
         st = m.speech_tokenizer if decode_audio else None
         wins = None
         if st is not None:
-            wins = [_StreamWindow(self, st, None if ref_codes is None else ref_codes[b], chunk_size, to_host) for b in range(B)]
+            wins = [self._make_window(st, None if ref_codes is None else ref_codes[b], chunk_size, to_host) for b in range(B)]
         kw = self._gen_kwargs(max_new_tokens, min_new_tokens, temperature, top_k, top_p, do_sample, repetition_penalty)
         for items in fast_generate_streaming_batch(
                 talker=m.talker, talker_input_embeds=tie, attention_mask=tam, trailing_text_hiddens=tth,

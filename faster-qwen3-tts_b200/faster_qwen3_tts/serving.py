@@ -174,7 +174,7 @@ def batcher_for_model(model, chunk_size: int = 8, to_host: bool = True) -> Conti
             return codes.cpu().numpy(), model.sample_rate
 
     def window(ref_codes):
-        return _StreamWindow(model, st, ref_codes, chunk_size, to_host) if st is not None else _CodesOnly()
+        return model._make_window(st, ref_codes, chunk_size, to_host) if st is not None else _CodesOnly()
 
     bd = (lambda wins, chunks: decode_windows_batched(st, wins, chunks)) if st is not None else None
     return ContinuousBatcher(sched, window, chunk_size=chunk_size, batch_decode=bd)

@@ -218,14 +218,29 @@ int fq3_codec_load_frontend(fq3_codec* c, const int32_t* geom, int32_t n_geom, c
  * launched.  Requires fq3_codec_load_weights + fq3_codec_load_frontend. */
 int fq3_codec_decode_codes(fq3_codec* c, const int64_t* codes_dev, int32_t batch, int32_t T, float* pcm_out_dev,
                            void* stream);
+/* Stateful streaming decode (replaces the reference's Phase-1 re-decode of everything so far and
+ * its 25-frame Phase-2 context window, model.py:1085-1135): a stream keeps, for every causal layer, the tail of that
+ * layer's input (conv history rows, the last window-1 attention keys / values), so a chunk of T frames costs T frames.
+ * The PCM of a stream equals the one-shot decode of the same codes (the decoder is causal).
+ * fq3_codec_stream_decode: the next T frames of n_streams distinct streams in one set of launches; codes_dev int64
+ * [n_streams][T][Q]; pcm_out_dev float32 [n_streams][T * total_upsample] or NULL (state warm-up only, e.g. the ICL
+ * reference frames). */
+typedef struct fq3_codec_stream fq3_codec_stream;
+int fq3_codec_stream_create(fq3_codec* c, fq3_codec_stream** out);
+int fq3_codec_stream_reset(fq3_codec_stream* s, void* stream);
+void fq3_codec_stream_destroy(fq3_codec_stream* s);
+int64_t fq3_codec_stream_frames(fq3_codec_stream* s);
+int fq3_codec_stream_decode(fq3_codec* c, fq3_codec_stream* const* streams, int32_t n_streams, const int64_t* codes_dev,
+                            int32_t T, float* pcm_out_dev, void* stream);
 double fq3_codec_flops(fq3_codec* c, int32_t T4);
 double fq3_codec_frontend_flops(fq3_codec* c, int32_t T);
 int64_t fq3_codec_launch_count(fq3_codec* c);
 void fq3_codec_destroy(fq3_codec* c);
 const char* fq3_codec_last_error(void);
 
-/* dense-layer kernel selection for K3/K4: 0 = tcgen05 + TMA implicit GEMM when the shape allows (default),
- * 1 = always the mma.sync kernel (A/B reference). */
+/* dense-layer kernel selection for K3/K4: 0 = tcgen05 + TMA implicit GEMM, one tile per CTA, when the shape allows
+ * (default); 1 = always the mma.sync kernel; 2 = persistent tcgen05 kernel with a double-buffered TMEM accumulator
+ * (1, 2: A/B references). */
 int fq3_set_gemm_backend(int32_t backend);
 
 const char* fq3_last_error(void);

@@ -133,3 +133,71 @@ def test_engine_decode_launches_no_library_kernel(full_codec):
     print(sorted(set(kernels)))
     foreign = [n for n in kernels if not any(s in n for s in ("fe::", "conv_gemm", "conv_out_kernel", "fq3", "cast_strided"))]
     assert not foreign, foreign
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# stateful streaming codec: a stream's PCM equals the one-shot decode of the same codes
+# ---------------------------------------------------------------------------------------------------------------------
+def test_stateful_stream_equals_one_shot_decode(full_codec):
+    """chunks of irregular sizes (incl. 1 frame and a chunk longer than the 72-frame attention window) pushed through one
+    stream == fq3_codec_decode_codes of the whole sequence: every output row is the same arithmetic (causal model), so
+    the bar is bit equality; the fp32 oracle bounds it at 1e-3 like every other codec path."""
+    st = full_codec
+    g = torch.Generator().manual_seed(21)
+    sizes = [8, 8, 3, 1, 12, 80, 8]
+    codes = torch.randint(0, 2048, (sum(sizes), 16), generator=g).cuda()
+    whole, _ = st.decode({"audio_codes": codes[None]})
+    stream = st.open_stream()
+    got, pos = [], 0
+    for n in sizes:
+        got.append(stream.push(codes[pos:pos + n]))
+        pos += n
+        assert stream.frames == pos
+    got = torch.cat(got)
+    d = (got - whole[0]).abs().max().item()
+    print(f"stream vs one-shot: max|d| = {d:.3e} over {got.numel()} samples")
+    assert got.shape == whole[0].shape
+    assert d == 0.0
+    want = _oracle(st, codes)
+    assert (got - want).abs().max().item() < TOL
+    # reset -> the same stream object reproduces the beginning
+    stream.reset()
+    again = stream.push(codes[:8])
+    assert torch.equal(again, got[: 8 * 1920])
+
+
+def test_stateful_streams_batched_at_different_positions(full_codec):
+    """three streams with different histories (fresh / 5 frames / 100 frames, the last one warmed without producing
+    audio) advance 8 frames in ONE call; every row equals the tail of its own one-shot decode."""
+    st = full_codec
+    g = torch.Generator().manual_seed(22)
+    hist = [0, 5, 100]
+    seqs = [torch.randint(0, 2048, (h + 8, 16), generator=g).cuda() for h in hist]
+    streams = [st.open_stream() for _ in hist]
+    for s, q, h in zip(streams, seqs, hist):
+        if h == 100:
+            s.warm(q[:h])
+        elif h:
+            s.push(q[:h])
+    out = st.push_streams(streams, torch.stack([q[-8:] for q in seqs]))
+    for s, q, h, pcm in zip(streams, seqs, hist, out):
+        whole, _ = st.decode({"audio_codes": q[None]})
+        assert torch.equal(pcm, whole[0][h * 1920:]), h
+        assert s.frames == h + 8
+
+
+def test_stateful_window_policy_streams_the_non_streaming_audio(full_codec):
+    """model-level: streaming_codec="stateful" through FasterQwen3TTS._stream_audio with an ICL reference of 174 frames:
+    the concatenated chunks equal the non-streaming decode + reference trim (model.py:918-938) of the same codes."""
+    import types
+    from faster_qwen3_tts.model import FasterQwen3TTS
+    st = full_codec
+    g = torch.Generator().manual_seed(23)
+    ref = torch.randint(0, 2048, (174, 16), generator=g).cuda()
+    chunks = [torch.randint(0, 2048, (8, 16), generator=g).cuda() for _ in range(5)] + [torch.randint(0, 2048, (3, 16), generator=g).cuda()]
+    owner = types.SimpleNamespace(streaming_codec="stateful", _to_numpy=FasterQwen3TTS._to_numpy)
+    owner._make_window = types.MethodType(FasterQwen3TTS._make_window, owner)
+    parts = [a for a, sr, _ in FasterQwen3TTS._stream_audio(owner, ((c, {}) for c in chunks), st, ref, 8, to_host=False)]
+    assert [p.shape[0] for p in parts] == [c.shape[0] * 1920 for c in chunks]
+    whole, _ = st.decode({"audio_codes": torch.cat([ref] + chunks)[None]})
+    assert torch.equal(torch.cat(parts), whole[0][174 * 1920:])

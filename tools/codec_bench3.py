@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Codec decode (codes -> PCM through fq3_codec_decode_codes) timed with CUDA events for the GEMM variants:
-persistent tcgen05 (default), one-tile-per-CTA tcgen05 (round 1), mma.sync; reports ms, TFLOP/s of the dense layers and
-the max PCM difference between variants.  python tools/codec_bench3.py [--variants tcgen05,tcgen05_1tile,mma]"""
+one-tile-per-CTA tcgen05 (default), persistent tcgen05, mma.sync; reports ms, TFLOP/s of the dense layers and
+the max PCM difference between variants.  python tools/codec_bench3.py [--variants tcgen05,tcgen05_persistent,mma]"""
 import argparse
 import json
 import os
@@ -15,7 +15,7 @@ from faster_qwen3_tts.codec import build_codec  # noqa: E402
 from faster_qwen3_tts.engine import set_gemm_backend  # noqa: E402
 
 ap = argparse.ArgumentParser()
-ap.add_argument("--variants", default="tcgen05,tcgen05_1tile")
+ap.add_argument("--variants", default="tcgen05,tcgen05_persistent")
 ap.add_argument("--cases", default="1x33,1x182,32x33,8x33")
 a = ap.parse_args()
 st = build_codec(dtype=torch.bfloat16, device="cuda", seed=1)

@@ -47,9 +47,9 @@ def launches(path, comment):
         t[name] += v
         n[name] += 1
     tot = sum(t.values())
-    OURS = ("fq3", "pf::", "to_channels_last_kernel", "conv_out_kernel", "set_state_kernel", "get_hidden_kernel",
-            "sample_kernel", "pack_kernel", "pack_mma_kernel", "mtp_table_kernel")
-    ours = sum(v for k, v in t.items() if k.startswith(OURS))
+    OURS = ("fq3", "pf::", "fe::", "to_channels_last_kernel", "conv_out_kernel", "conv_gemm", "set_state_kernel",
+            "get_hidden_kernel", "sample_kernel", "pack_kernel", "pack_mma_kernel", "mtp_table_kernel", "cast_strided")
+    ours = sum(v for k, v in t.items() if any(s in k for s in OURS))
     print(f"# {comment}")
     print(f"# {sum(n.values())} launches, {tot / 1e3:.1f} ms total device time; hand-written kernels {100 * ours / tot:.1f}% of device time.")
     print("# per-launch times are cold-cache and serialised under ncu: compare SHARES, not absolutes")
