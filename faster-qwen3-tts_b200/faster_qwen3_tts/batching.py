@@ -148,7 +148,7 @@ def fast_generate_streaming_batch(
                 continue
             totals[rq.tag] += n
             tm = {"chunk_index": idx, "chunk_steps": n, "prefill_ms": t_prefill * 1000 if idx == 0 else 0,
-                  "decode_ms": dt * 1000, "total_steps_so_far": totals[rq.tag], "is_final": n < chunk_size}
+                  "decode_ms": dt * 1000, "total_steps_so_far": totals[rq.tag], "is_final": n < chunk_size or rq.finished == 3}
             if engine.time_kernels:
                 tm["kernel_ms"] = engine.last_kernel_ms
             items.append((rq.tag, codes, tm))

@@ -86,7 +86,9 @@ def begin_fused(engine, talker, tie, tam, tth, tpe, config, predictor_graph, tal
 def stepwise_frames(talker, tie, tam, tth, tpe, config, predictor_graph, talker_graph, *, max_new_tokens,
                     min_new_tokens, temperature, top_k, top_p, do_sample, repetition_penalty):
     """Generator over frames for arbitrary duck-typed graphs (compatibility path; one host round trip per frame).
-    Yields ("prefill_done", None) once, then ("frame", LongTensor[16]) per emitted frame."""
+    Yields ("prefill_done", None) once, then per emitted frame ("frame", LongTensor[16]) and, once the talker step that
+    follows it has been taken, ("step_done", None) -- a frame whose step is cut short by the cache limit
+    (generate.py:175-177) has no "step_done"."""
     eos_id = config.codec_eos_token_id
     n_groups = config.num_code_groups
     smask = special_suppress_mask(config.vocab_size, eos_id, tie.device)
@@ -121,6 +123,7 @@ def stepwise_frames(talker, tie, tam, tth, tpe, config, predictor_graph, talker_
         token = sample_logits(logits.squeeze(0), suppress_tokens=[eos_id] if len(history) < min_new_tokens else None, **kw)
         past_hidden = hidden[:, -1:, :].clone()
         gen_step += 1
+        yield "step_done", None
 
 
 def _sync(device):
@@ -185,7 +188,7 @@ def fast_generate(
                 _sync(device)
                 t_prefill = time.time() - t0
                 t1 = time.time()
-            else:
+            elif kind == "frame":
                 frames.append(row)
         _sync(device)
         t_decode = time.time() - t1

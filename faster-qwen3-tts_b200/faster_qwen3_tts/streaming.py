@@ -57,7 +57,9 @@ def fast_generate_streaming(
             n = res.frames_emitted
             if n:
                 total += n
-                tm = _timing(idx, n, t_prefill, time.time() - t1, total, n < chunk_size)
+                # the reference flags the trailing partial chunk -- and a full chunk cut off by the cache limit, which
+                # leaves its loop before the "buffer full" check (streaming.py:130-132 vs :158-173)
+                tm = _timing(idx, n, t_prefill, time.time() - t1, total, n < chunk_size or res.finished == 3)
                 if engine.time_kernels:
                     tm["kernel_ms"] = engine.last_kernel_ms
                 yield codes.clone(), tm
@@ -72,8 +74,10 @@ def fast_generate_streaming(
 
 
 def _chunked(frames, device, chunk_size, t0):
-    """Shared chunker of the host-driven paths: frames -> (codes [n,16], timing) with the reference's timing keys; a
-    partial last chunk is the only one flagged is_final (streaming.py:162-188)."""
+    """Shared chunker of the host-driven paths: frames -> (codes [n,16], timing) with the reference's timing keys.  A
+    full buffer is flushed (is_final False) when the step after its last frame completes; whatever is left when the
+    generator ends -- a partial chunk, or a full one whose last step hit the cache limit -- is flagged is_final
+    (streaming.py:158-188)."""
     buf, t_prefill, t1, total, idx = [], 0.0, t0, 0, 0
     for kind, row in frames:
         if kind == "prefill_done":
@@ -81,8 +85,10 @@ def _chunked(frames, device, chunk_size, t0):
             t_prefill = time.time() - t0
             t1 = time.time()
             continue
-        buf.append(row)
-        if len(buf) >= chunk_size:
+        if kind == "frame":
+            buf.append(row)
+            continue
+        if len(buf) >= chunk_size:   # "step_done"
             _sync(device)
             total += len(buf)
             yield torch.stack(buf), _timing(idx, len(buf), t_prefill, time.time() - t1, total, False)
@@ -130,6 +136,7 @@ def _dynamic_cache_frames(talker, tie, tam, tth, tpe, config, *, max_new_tokens,
         if repetition_penalty != 1.0:
             logits = apply_repetition_penalty(logits, torch.stack(history), repetition_penalty)
         token = sample_logits(logits, suppress_tokens=[eos_id] if len(history) < min_new_tokens else None, **kw)
+        yield "step_done", None
 
 
 @torch.inference_mode()

@@ -233,16 +233,18 @@ def gen_loop(ref, out_path):
         codes = torch.zeros(0, 16, dtype=torch.long) if codes is None else codes
         # streaming
         proxy.uniforms = [float(x) for x in uniforms[:, 0]]
-        chunks, keys = [], None
+        chunks, keys, finals = [], None, []
         for c, t in ref["streaming"].fast_generate_streaming(
                 talker=_Talker(om), predictor_graph=_PredGraph(om, sp_pred, uniforms),
                 talker_graph=_TalkerGraph(om, max_seq), chunk_size=chunk, **kw):
             chunks.append(c)
+            finals.append(int(t["is_final"]))
             keys = sorted(t.keys())
         scodes = torch.cat(chunks) if chunks else torch.zeros(0, 16, dtype=torch.long)
         assert torch.equal(scodes, codes), name
         out[name + "_codes"] = codes.numpy()
         out[name + "_chunks"] = np.array([c.shape[0] for c in chunks], dtype=np.int64)
+        out[name + "_final"] = np.array(finals, dtype=np.int64)
         out[name + "_params"] = np.array([wseed, P, Tt, max_new, min_new, int(do_sample), pen, max_seq, chunk, boost,
                                           nseed], dtype=np.float64)
         eos_hit = codes.shape[0] < max_new

@@ -158,14 +158,16 @@ def test_fused_loop_vs_reference_scheduler_goldens(idx, golden_dir):
     assert codes.shape == want.shape and np.array_equal(codes.numpy(), want), name
     assert set(timing) == {"prefill_ms", "decode_s", "steps", "ms_per_step", "steps_per_s"}
     # streaming: same tokens, reference chunk boundaries and timing keys
-    chunks = []
+    chunks, finals = [], []
     u = torch.from_numpy(uniforms).cuda()
     for c, t in fast_generate_streaming(p.talker, tie[None].cuda(), torch.ones(1, int(P), dtype=torch.long).cuda(),
                                         tth[None].cuda(), tpe[None, None].cuda(), p.config, p.pg, p.tg,
                                         chunk_size=int(chunk), uniforms=u, **kw):
         chunks.append(c.cpu())
+        finals.append(int(t["is_final"]))
         assert set(t) == {"chunk_index", "chunk_steps", "prefill_ms", "decode_ms", "total_steps_so_far", "is_final"}
     assert [c.shape[0] for c in chunks] == loop[name + "_chunks"].tolist()
+    assert finals == loop[name + "_final"].tolist()   # incl. the FULL last chunk the cache limit makes final
     if chunks:
         assert np.array_equal(torch.cat(chunks).numpy(), want)
 
