@@ -44,6 +44,18 @@ int cfail(int code, const char* msg, const char* extra = "") {
 
 using namespace fq3gemm;
 
+// the caller's current device is restored when an entry point returns (single-process multi-GPU hosts, torch)
+struct CodecDevGuard {
+  int prev = -1, dev;
+  explicit CodecDevGuard(int d) : dev(d) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != dev) cudaSetDevice(dev);
+  }
+  ~CodecDevGuard() {
+    if (prev >= 0 && prev != dev) cudaSetDevice(prev);
+  }
+};
+
 // final causal conv7 (C -> 1) over activated input + clamp to [-1, 1]; one thread per output sample
 __global__ void conv_out_kernel(const __nv_bfloat16* __restrict__ X, const float* __restrict__ W, float bias, int T,
                                 int C, int taps, float* __restrict__ out, int x_row0, int x_rows) {
@@ -365,7 +377,7 @@ extern "C" int fq3_codec_create(const int32_t* geom, int32_t n_geom, fq3_codec**
   if (c->n_blocks < 1 || c->n_blocks > 8 || n_geom < 4 + c->n_blocks) { delete c; return cfail(FQ3_ERR_INVALID, "bad codec geometry"); }
   for (int i = 0; i < c->n_blocks; ++i) c->rates[i] = geom[4 + i];
   if (c->hidden % BK || c->decoder_dim % (BK << c->n_blocks)) { delete c; return cfail(FQ3_ERR_INVALID, "codec channels must be multiples of 32 at every level"); }
-  CCK(cudaSetDevice(c->dev));
+  CodecDevGuard dev_guard(c->dev);
   CCK(cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CONV_SMEM));
   *out = c;
   return 0;
@@ -373,7 +385,7 @@ extern "C" int fq3_codec_create(const int32_t* geom, int32_t n_geom, fq3_codec**
 
 extern "C" void fq3_codec_destroy(fq3_codec* c) {
   if (!c) return;
-  cudaSetDevice(c->dev);
+  CodecDevGuard dev_guard(c->dev);
   for (void* p : c->owned) cudaFree(p);
   for (auto* b : c->buf) if (b) cudaFree(b);
   for (auto* b : c->fe.buf) if (b) cudaFree(b);
@@ -389,7 +401,7 @@ extern "C" void fq3_codec_destroy(fq3_codec* c) {
 //   out.act.a out.act.b [C]   out.w [1,C,7] out.b [1]
 extern "C" int fq3_codec_load_weights(fq3_codec* c, const fq3_tensor* tensors, int32_t n, void* stream_) {
   if (!c || !tensors) return cfail(FQ3_ERR_INVALID, "null argument");
-  CCK(cudaSetDevice(c->dev));
+  CodecDevGuard dev_guard(c->dev);
   cudaStream_t stream = (cudaStream_t)stream_;
   std::map<std::string, const fq3_tensor*> tm;
   for (int i = 0; i < n; ++i) tm[tensors[i].name] = &tensors[i];
@@ -603,7 +615,7 @@ extern "C" int fq3_codec_decode_batch(fq3_codec* c, const void* x_dev, int32_t b
                                       void* stream_) {
   if (!c || !x_dev || !pcm_out_dev || T4 <= 0 || batch <= 0) return cfail(FQ3_ERR_INVALID, "null argument");
   if (c->layers.empty()) return cfail(FQ3_ERR_STATE, "codec weights not loaded");
-  CCK(cudaSetDevice(c->dev));
+  CodecDevGuard dev_guard(c->dev);
   cudaStream_t stream = (cudaStream_t)stream_;
   int rc;
   if ((rc = stack_reserve(c, batch, T4))) return rc;
@@ -636,7 +648,7 @@ static __global__ void cast_strided_kernel(const float* __restrict__ src, __nv_b
 extern "C" int fq3_codec_load_frontend(fq3_codec* c, const int32_t* geom, int32_t n_geom, const float* fgeom,
                                        int32_t n_fgeom, const fq3_tensor* tensors, int32_t n, void* stream_) {
   if (!c || !geom || !fgeom || !tensors || n_geom < 8 || n_fgeom < 2) return cfail(FQ3_ERR_INVALID, "null argument");
-  CCK(cudaSetDevice(c->dev));
+  CodecDevGuard dev_guard(c->dev);
   cudaStream_t stream = (cudaStream_t)stream_;
   FrontEnd& f = c->fe;
   f.ready = false;
@@ -775,7 +787,7 @@ extern "C" int fq3_codec_decode_codes(fq3_codec* c, const int64_t* codes_dev, in
   if (c->layers.empty()) return cfail(FQ3_ERR_STATE, "codec weights not loaded");
   FrontEnd& f = c->fe;
   if (!f.ready) return cfail(FQ3_ERR_STATE, "fq3_codec_load_frontend has not been called");
-  CCK(cudaSetDevice(c->dev));
+  CodecDevGuard dev_guard(c->dev);
   cudaStream_t stream = (cudaStream_t)stream_;
   const int H = f.H, I = f.I, hd = H / f.nh;
   const size_t rows0 = (size_t)batch * T;
@@ -886,7 +898,7 @@ static int stream_sites(fq3_codec* c) {
 extern "C" int fq3_codec_stream_create(fq3_codec* c, fq3_codec_stream** out) {
   if (!c || !out) return cfail(FQ3_ERR_INVALID, "null argument");
   if (c->layers.empty() || !c->fe.ready) return cfail(FQ3_ERR_STATE, "codec weights / front end not loaded");
-  CCK(cudaSetDevice(c->dev));
+  CodecDevGuard dev_guard(c->dev);
   stream_sites(c);
   fq3_codec_stream* s = new fq3_codec_stream();
   s->owner = c;
@@ -897,14 +909,14 @@ extern "C" int fq3_codec_stream_create(fq3_codec* c, fq3_codec_stream** out) {
 }
 extern "C" int fq3_codec_stream_reset(fq3_codec_stream* s, void* stream_) {
   if (!s) return cfail(FQ3_ERR_INVALID, "null argument");
-  CCK(cudaSetDevice(s->owner->dev));
+  CodecDevGuard dev_guard(s->owner->dev);
   CCK(cudaMemsetAsync(s->tails, 0, s->owner->tail_elems * 2, (cudaStream_t)stream_));
   s->frames = 0;
   return 0;
 }
 extern "C" void fq3_codec_stream_destroy(fq3_codec_stream* s) {
   if (!s) return;
-  cudaSetDevice(s->owner->dev);
+  CodecDevGuard dev_guard(s->owner->dev);
   cudaFree(s->tails);
   delete s;
 }
@@ -923,7 +935,7 @@ extern "C" int fq3_codec_stream_decode(fq3_codec* c, fq3_codec_stream* const* st
     for (int a = 0; a < b; ++a)
       if (streams[a] == streams[b]) return cfail(FQ3_ERR_INVALID, "stream listed twice");
   }
-  CCK(cudaSetDevice(c->dev));
+  CodecDevGuard dev_guard(c->dev);
   cudaStream_t stream = (cudaStream_t)stream_;
   stream_sites(c);
   const int batch = n_streams;
