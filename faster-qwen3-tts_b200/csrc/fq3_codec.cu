@@ -59,6 +59,8 @@ struct CodecDevGuard {
 // final causal conv7 (C -> 1) over activated input + clamp to [-1, 1]; one thread per output sample
 __global__ void conv_out_kernel(const __nv_bfloat16* __restrict__ X, const float* __restrict__ W, float bias, int T,
                                 int C, int taps, float* __restrict__ out, int x_row0, int x_rows) {
+  pdl_launch();
+  pdl_wait();
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= T) return;
   X += (size_t)blockIdx.y * x_rows * C;  // blockIdx.y = sequence of the batch; its input has x_row0 history rows in front
@@ -113,6 +115,8 @@ __global__ void embed_mean_kernel(const long long* __restrict__ codes, const __n
                                   int codebook, int H, __nv_bfloat16* __restrict__ X) {
   const size_t row = blockIdx.x;
   __shared__ long long ids[64];
+  fq3gemm::pdl_launch();
+  fq3gemm::pdl_wait();
   if ((int)threadIdx.x < Q) {
     long long c = codes[row * Q + threadIdx.x];
     c = c < 0 ? 0 : (c >= codebook ? codebook - 1 : c);
@@ -130,6 +134,8 @@ __global__ void embed_mean_kernel(const long long* __restrict__ codes, const __n
 __global__ void rmsnorm_rows_kernel(const __nv_bfloat16* __restrict__ X, const float* __restrict__ w, int H, float eps,
                                     __nv_bfloat16* __restrict__ Y) {
   __shared__ float red[8];
+  fq3gemm::pdl_launch();
+  fq3gemm::pdl_wait();
   const size_t row = blockIdx.x;
   const int tid = threadIdx.x;
   float v[8];
@@ -159,6 +165,8 @@ __global__ void rmsnorm_rows_kernel(const __nv_bfloat16* __restrict__ X, const f
 // hd <= 128, rotate_half convention: o[e] = x[e] cos - x[e + hd/2] sin, o[e + hd/2] = x[e + hd/2] cos + x[e] sin
 __global__ void rope_qk_kernel(__nv_bfloat16* __restrict__ QKV, int rows, int T, int nh, int hd,
                                const float* __restrict__ inv_freq, const int* __restrict__ pos0) {
+  fq3gemm::pdl_launch();
+  fq3gemm::pdl_wait();
   const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (gw >= rows * nh * 2) return;
   const int row = gw / (nh * 2), r = gw % (nh * 2), which = r / nh, h = r % nh;
@@ -183,6 +191,8 @@ __global__ void __launch_bounds__(256) swa_kernel(const __nv_bfloat16* __restric
                                                   __nv_bfloat16* __restrict__ OUT, int x_rows, int row0,
                                                   const int* __restrict__ valid) {
   extern __shared__ float fsm[];
+  fq3gemm::pdl_launch();
+  fq3gemm::pdl_wait();
   const int Wpad = (W + 31) & ~31;
   float* sc = fsm;                  // [8][Wpad]
   float* qs = fsm + 8 * Wpad;       // [8][HD]
@@ -251,6 +261,8 @@ __global__ void dwconv_ln_kernel(const __nv_bfloat16* __restrict__ X, int T, int
                                  const float* __restrict__ bias, const float* __restrict__ lnw, const float* __restrict__ lnb,
                                  float eps, __nv_bfloat16* __restrict__ Y, int x_row0, int x_rows) {
   __shared__ float red[2][8];
+  fq3gemm::pdl_launch();
+  fq3gemm::pdl_wait();
   const size_t row = blockIdx.x;
   const int t = (int)(row % T) + x_row0;                                  // row inside the sequence's input block
   const size_t xrow = (row / T) * (size_t)x_rows + t;
@@ -548,7 +560,7 @@ static int launch_conv(fq3_codec* c, const Layer& L, const __nv_bfloat16* X, con
     if (r < 0) return cfail(FQ3_ERR_CUDA, "tcgen05 conv launch failed: ", cudaGetErrorString(cudaGetLastError()));
   }
   dim3 grid(((T + BM - 1) / BM) * batch, (L.N + BN - 1) / BN);
-  conv_gemm_kernel<<<grid, CTHREADS, CONV_SMEM, stream>>>(a);
+  FQ3_LAUNCH((conv_gemm_kernel), grid, CTHREADS, CONV_SMEM, stream, a);
   CCK(cudaGetLastError());
   return 0;
 }
@@ -603,7 +615,7 @@ static int stack_run(fq3_codec* c, const __nv_bfloat16* xcl, int batch, int T4, 
     cur = a1;
   }
   __nv_bfloat16* act = cur;
-  conv_out_kernel<<<dim3((T + 255) / 256, batch), 256, 0, stream>>>(act, c->w_out, c->b_out, T, c->c_out, 7, pcm_out_dev, 0, T);
+  FQ3_LAUNCH((conv_out_kernel), dim3((T + 255) / 256, batch), 256, 0, stream, act, c->w_out, c->b_out, T, c->c_out, 7, pcm_out_dev, 0, T);
   c->launches++;
   CCK(cudaGetLastError());
   return 0;
@@ -774,7 +786,7 @@ static int fe_gemm(fq3_codec* c, const __nv_bfloat16* X, const __nv_bfloat16* W,
     if (r < 0) return cfail(FQ3_ERR_CUDA, "tcgen05 GEMM launch failed: ", cudaGetErrorString(cudaGetLastError()));
   }
   dim3 grid((rows + BM - 1) / BM, (N + BN - 1) / BN);
-  conv_gemm_kernel<<<grid, CTHREADS, CONV_SMEM, stream>>>(a);
+  FQ3_LAUNCH((conv_gemm_kernel), grid, CTHREADS, CONV_SMEM, stream, a);
   CCK(cudaGetLastError());
   return 0;
 }
@@ -804,31 +816,31 @@ extern "C" int fq3_codec_decode_codes(fq3_codec* c, const int64_t* codes_dev, in
   if ((rc = stack_reserve(c, batch, (int)(T * up)))) return rc;
   __nv_bfloat16 *A = f.buf[0], *Bx = f.buf[1], *Cn = f.buf[2], *D = f.buf[3], *E = f.buf[4];
   const int R0 = (int)rows0;
-  fe::embed_mean_kernel<<<R0, 256, 0, stream>>>((const long long*)codes_dev, f.emb, f.Q, f.codebook, H, A);
+  FQ3_LAUNCH((fe::embed_mean_kernel), R0, 256, 0, stream, (const long long*)codes_dev, f.emb, f.Q, f.codebook, H, A);
   c->launches++;
   const int Wpad = (f.window + 31) & ~31;
   const size_t swa_smem = (size_t)(8 * Wpad + 8 * hd) * sizeof(float);
   if (swa_smem > 96 * 1024) return cfail(FQ3_ERR_INVALID, "sliding window too large");
   for (int l = 0; l < f.L; ++l) {
     const FeLayer& y = f.layers[l];
-    fe::rmsnorm_rows_kernel<<<R0, 256, 0, stream>>>(A, y.ln1, H, f.eps, Cn);
+    FQ3_LAUNCH((fe::rmsnorm_rows_kernel), R0, 256, 0, stream, A, y.ln1, H, f.eps, Cn);
     if ((rc = fe_gemm(c, Cn, y.qkv, nullptr, nullptr, nullptr, D, R0, H, 3 * H, 1, 0, stream))) return rc;
     {
       const long long warps = (long long)R0 * f.nh * 2;
-      fe::rope_qk_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, stream>>>(D, R0, T, f.nh, hd, f.inv_freq, nullptr);
+      FQ3_LAUNCH((fe::rope_qk_kernel), (unsigned)((warps * 32 + 255) / 256), 256, 0, stream, D, R0, T, f.nh, hd, f.inv_freq, nullptr);
     }
     {
       dim3 g((T + 7) / 8, f.nh, batch);
-      if (hd == 64) fe::swa_kernel<64><<<g, 256, swa_smem, stream>>>(D, T, f.nh, f.window, E, T, 0, nullptr);
-      else fe::swa_kernel<128><<<g, 256, swa_smem, stream>>>(D, T, f.nh, f.window, E, T, 0, nullptr);
+      if (hd == 64) FQ3_LAUNCH((fe::swa_kernel<64>), g, 256, swa_smem, stream, D, T, f.nh, f.window, E, T, 0, nullptr);
+      else FQ3_LAUNCH((fe::swa_kernel<128>), g, 256, swa_smem, stream, D, T, f.nh, f.window, E, T, 0, nullptr);
     }
     if ((rc = fe_gemm(c, E, y.o, nullptr, y.s1, A, Bx, R0, H, H, 1, 0, stream))) return rc;
-    fe::rmsnorm_rows_kernel<<<R0, 256, 0, stream>>>(Bx, y.ln2, H, f.eps, Cn);
+    FQ3_LAUNCH((fe::rmsnorm_rows_kernel), R0, 256, 0, stream, Bx, y.ln2, H, f.eps, Cn);
     if ((rc = fe_gemm(c, Cn, y.gu, nullptr, nullptr, nullptr, D, R0, H, 2 * I, 1, 1, stream))) return rc;
     if ((rc = fe_gemm(c, D, y.down, nullptr, y.s2, Bx, A, R0, I, H, 1, 0, stream))) return rc;
     c->launches += 4;
   }
-  fe::rmsnorm_rows_kernel<<<R0, 256, 0, stream>>>(A, f.norm, H, f.eps, Cn);
+  FQ3_LAUNCH((fe::rmsnorm_rows_kernel), R0, 256, 0, stream, A, f.norm, H, f.eps, Cn);
   c->launches++;
   __nv_bfloat16* cur = Cn;
   int rows = R0, Tc = T;
@@ -839,7 +851,7 @@ extern "C" int fq3_codec_decode_codes(fq3_codec* c, const int64_t* codes_dev, in
     if ((rc = fe_gemm(c, cur, y.ct, y.ct_b, nullptr, nullptr, A, rows, H, y.r * H, H, 0, stream))) return rc;
     rows *= y.r;
     Tc *= y.r;
-    fe::dwconv_ln_kernel<<<rows, 256, 0, stream>>>(A, Tc, H, y.dw_w, y.dw_b, y.ln_w, y.ln_b, 1e-6f, Bx, 0, Tc);
+    FQ3_LAUNCH((fe::dwconv_ln_kernel), rows, 256, 0, stream, A, Tc, H, y.dw_w, y.dw_b, y.ln_w, y.ln_b, 1e-6f, Bx, 0, Tc);
     c->launches++;
     if ((rc = fe_gemm(c, Bx, y.pw1, y.pw1_b, nullptr, nullptr, D, rows, H, 4 * H, 4 * H, 2, stream))) return rc;
     if ((rc = fe_gemm(c, D, y.pw2, y.pw2_b, y.gamma, A, out, rows, 4 * H, H, H, 0, stream))) return rc;
@@ -862,6 +874,8 @@ static __global__ void ext_build_kernel(const __nv_bfloat16* const* __restrict__
                                         const __nv_bfloat16* __restrict__ X, int h, int T, int C8,
                                         __nv_bfloat16* __restrict__ E) {
   // E[b][r][:] = r < h ? tail_b[r][:] : X[b][r - h][:]        (16-byte vectors; C8 = C / 8)
+  fq3gemm::pdl_launch();
+  fq3gemm::pdl_wait();
   const int b = blockIdx.y;
   const long long n = (long long)(h + T) * C8;
   const uint4* tb = reinterpret_cast<const uint4*>(tails[b] + off);
@@ -875,6 +889,8 @@ static __global__ void ext_build_kernel(const __nv_bfloat16* const* __restrict__
 static __global__ void tail_save_kernel(__nv_bfloat16* const* __restrict__ tails, size_t off,
                                         const __nv_bfloat16* __restrict__ E, int h, int T, int C8) {
   // tail_b <- last h rows of E[b]
+  fq3gemm::pdl_launch();
+  fq3gemm::pdl_wait();
   const int b = blockIdx.y;
   const long long n = (long long)h * C8;
   uint4* tb = reinterpret_cast<uint4*>(tails[b] + off);
@@ -997,9 +1013,9 @@ extern "C" int fq3_codec_stream_decode(fq3_codec* c, fq3_codec_stream* const* st
     const int C8 = st.C / 8;
     const long long n = (long long)(st.h + Tn) * C8;
     dim3 g((unsigned)std::min<long long>((n + 255) / 256, 1024), batch);
-    ext_build_kernel<<<g, 256, 0, stream>>>((const __nv_bfloat16* const*)c->d_tailptr, st.off, X, st.h, Tn, C8, c->ext);
+    FQ3_LAUNCH((ext_build_kernel), g, 256, 0, stream, (const __nv_bfloat16* const*)c->d_tailptr, st.off, X, st.h, Tn, C8, c->ext);
     dim3 g2((unsigned)std::min<long long>(((long long)st.h * C8 + 255) / 256, 256), batch);
-    tail_save_kernel<<<g2, 256, 0, stream>>>((__nv_bfloat16* const*)c->d_tailptr, st.off, c->ext, st.h, Tn, C8);
+    FQ3_LAUNCH((tail_save_kernel), g2, 256, 0, stream, (__nv_bfloat16* const*)c->d_tailptr, st.off, c->ext, st.h, Tn, C8);
     c->launches += 2;
     return c->ext;
   };
@@ -1007,32 +1023,32 @@ extern "C" int fq3_codec_stream_decode(fq3_codec* c, fq3_codec_stream* const* st
   // ---- front end
   __nv_bfloat16 *A = f.buf[0], *Bx = f.buf[1], *Cn = f.buf[2], *D = f.buf[3], *E = f.buf[4];
   const int R0 = (int)rows0;
-  fe::embed_mean_kernel<<<R0, 256, 0, stream>>>((const long long*)codes_dev, f.emb, f.Q, f.codebook, H, A);
+  FQ3_LAUNCH((fe::embed_mean_kernel), R0, 256, 0, stream, (const long long*)codes_dev, f.emb, f.Q, f.codebook, H, A);
   c->launches++;
   const int Wpad = (f.window + 31) & ~31;
   const size_t swa_smem = (size_t)(8 * Wpad + 8 * hd) * sizeof(float);
   for (int l = 0; l < f.L; ++l) {
     const FeLayer& y = f.layers[l];
-    fe::rmsnorm_rows_kernel<<<R0, 256, 0, stream>>>(A, y.ln1, H, f.eps, Cn);
+    FQ3_LAUNCH((fe::rmsnorm_rows_kernel), R0, 256, 0, stream, A, y.ln1, H, f.eps, Cn);
     if ((rc = fe_gemm(c, Cn, y.qkv, nullptr, nullptr, nullptr, D, R0, H, 3 * H, 1, 0, stream))) return rc;
     {
       const long long warps = (long long)R0 * f.nh * 2;
-      fe::rope_qk_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, stream>>>(D, R0, T, f.nh, hd, f.inv_freq, c->d_pos0);
+      FQ3_LAUNCH((fe::rope_qk_kernel), (unsigned)((warps * 32 + 255) / 256), 256, 0, stream, D, R0, T, f.nh, hd, f.inv_freq, c->d_pos0);
     }
     const int h = hist(site);
     const __nv_bfloat16* qkv = with_history(D, T);
     {
       dim3 g((T + 7) / 8, f.nh, batch);
-      if (hd == 64) fe::swa_kernel<64><<<g, 256, swa_smem, stream>>>(qkv, T, f.nh, f.window, E, h + T, h, c->d_valid);
-      else fe::swa_kernel<128><<<g, 256, swa_smem, stream>>>(qkv, T, f.nh, f.window, E, h + T, h, c->d_valid);
+      if (hd == 64) FQ3_LAUNCH((fe::swa_kernel<64>), g, 256, swa_smem, stream, qkv, T, f.nh, f.window, E, h + T, h, c->d_valid);
+      else FQ3_LAUNCH((fe::swa_kernel<128>), g, 256, swa_smem, stream, qkv, T, f.nh, f.window, E, h + T, h, c->d_valid);
     }
     if ((rc = fe_gemm(c, E, y.o, nullptr, y.s1, A, Bx, R0, H, H, 1, 0, stream))) return rc;
-    fe::rmsnorm_rows_kernel<<<R0, 256, 0, stream>>>(Bx, y.ln2, H, f.eps, Cn);
+    FQ3_LAUNCH((fe::rmsnorm_rows_kernel), R0, 256, 0, stream, Bx, y.ln2, H, f.eps, Cn);
     if ((rc = fe_gemm(c, Cn, y.gu, nullptr, nullptr, nullptr, D, R0, H, 2 * I, 1, 1, stream))) return rc;
     if ((rc = fe_gemm(c, D, y.down, nullptr, y.s2, Bx, A, R0, I, H, 1, 0, stream))) return rc;
     c->launches += 4;
   }
-  fe::rmsnorm_rows_kernel<<<R0, 256, 0, stream>>>(A, f.norm, H, f.eps, Cn);
+  FQ3_LAUNCH((fe::rmsnorm_rows_kernel), R0, 256, 0, stream, A, f.norm, H, f.eps, Cn);
   c->launches++;
   __nv_bfloat16* cur = Cn;
   int rows = R0, Tc = T;
@@ -1044,7 +1060,7 @@ extern "C" int fq3_codec_stream_decode(fq3_codec* c, fq3_codec_stream* const* st
     Tc *= y.r;
     const int h = hist(site);
     const __nv_bfloat16* xin = with_history(A, Tc);
-    fe::dwconv_ln_kernel<<<rows, 256, 0, stream>>>(xin, Tc, H, y.dw_w, y.dw_b, y.ln_w, y.ln_b, 1e-6f, Bx, h, h + Tc);
+    FQ3_LAUNCH((fe::dwconv_ln_kernel), rows, 256, 0, stream, xin, Tc, H, y.dw_w, y.dw_b, y.ln_w, y.ln_b, 1e-6f, Bx, h, h + Tc);
     c->launches++;
     if ((rc = fe_gemm(c, Bx, y.pw1, y.pw1_b, nullptr, nullptr, D, rows, H, 4 * H, 4 * H, 2, stream))) return rc;
     if ((rc = fe_gemm(c, D, y.pw2, y.pw2_b, y.gamma, A, out, rows, 4 * H, H, H, 0, stream))) return rc;
@@ -1082,7 +1098,7 @@ extern "C" int fq3_codec_stream_decode(fq3_codec* c, fq3_codec_stream* const* st
     const int h = hist(site);
     const __nv_bfloat16* xin = with_history(act, Ts);
     if (pcm_out_dev) {
-      conv_out_kernel<<<dim3((Ts + 255) / 256, batch), 256, 0, stream>>>(xin, c->w_out, c->b_out, Ts, c->c_out, 7, pcm_out_dev, h, h + Ts);
+      FQ3_LAUNCH((conv_out_kernel), dim3((Ts + 255) / 256, batch), 256, 0, stream, xin, c->w_out, c->b_out, Ts, c->c_out, 7, pcm_out_dev, h, h + Ts);
       c->launches++;
     }
   }

@@ -10,8 +10,44 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
 
 namespace fq3gemm {
+
+// ---- programmatic dependent launch (PDL): the K3 / K4 chains are hundreds of short dependent kernels; with
+// programmatic stream serialization kernel N+1 is scheduled as soon as every CTA of kernel N has started, runs its
+// prologue (barrier init, TMEM allocation, tensor-map prefetch, parameter staging) and blocks in griddepcontrol.wait
+// until kernel N has completed and flushed its memory -- launch latency and prologue leave the critical path, memory
+// semantics are those of ordinary stream order.  Every kernel launched through launch_pdl() calls pdl_wait() before
+// its first access to memory another kernel may have written.  FQ3_NO_PDL=1 launches them plainly (A/B).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+static inline bool pdl_enabled() {
+  static const bool on = [] {
+    const char* v = getenv("FQ3_NO_PDL");
+    return !(v && atoi(v) != 0);
+  }();
+  return on;
+}
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                     Args... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#define FQ3_LAUNCH(kernel, grid, block, smem, stream, ...) \
+  fq3gemm::launch_pdl(kernel, dim3(grid), dim3(block), (size_t)(smem), stream, __VA_ARGS__)
 
 constexpr int BM = 128, BN = 96, BK = 32, STAGES = 4, CTHREADS = 256;
 constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;
@@ -65,6 +101,8 @@ __device__ __forceinline__ int swz(int row, int chunk) { return row * 64 + ((chu
 static __global__ void __launch_bounds__(CTHREADS, 2) conv_gemm_kernel(  // static: included by two TUs
     const __grid_constant__ ConvArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
+  pdl_launch();
+  pdl_wait();
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * A_BYTES;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;

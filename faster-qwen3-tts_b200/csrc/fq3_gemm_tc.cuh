@@ -196,6 +196,8 @@ static __global__ void __launch_bounds__(TTHREADS, DEEP ? 1 : 2)
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = *tmem_slot;
+  fq3gemm::pdl_launch();   // the next kernel of the chain may start its own prologue ...
+  fq3gemm::pdl_wait();     // ... and this one touches activations only after its predecessor has completed
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -314,6 +316,8 @@ static __global__ void __launch_bounds__(TTHREADS, 1)
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = *tmem_slot;
+  fq3gemm::pdl_launch();   // the next kernel of the chain may start its own prologue ...
+  fq3gemm::pdl_wait();     // ... and this one touches activations only after its predecessor has completed
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -504,17 +508,17 @@ static int launch_tc(const fq3gemm::ConvArgs& a, cudaStream_t stream, int varian
   const long long ntiles = (long long)grid.x * grid.y;
   if (variant == 2 && ntiles > num_sms && ntiles < (1ll << 30)) {
     const int tiles_m = (a.T + TBM - 1) / TBM;
-    if (BK == 64) conv_gemm_tcp_kernel<64><<<num_sms, TTHREADS, PCfg<64>::SMEM, stream>>>(tmX, tmW, a, tiles_m, tiles_m * nb, (int)ntiles);
-    else conv_gemm_tcp_kernel<32><<<num_sms, TTHREADS, PCfg<32>::SMEM, stream>>>(tmX, tmW, a, tiles_m, tiles_m * nb, (int)ntiles);
+    if (BK == 64) FQ3_LAUNCH((conv_gemm_tcp_kernel<64>), num_sms, TTHREADS, PCfg<64>::SMEM, stream, tmX, tmW, a, tiles_m, tiles_m * nb, (int)ntiles);
+    else FQ3_LAUNCH((conv_gemm_tcp_kernel<32>), num_sms, TTHREADS, PCfg<32>::SMEM, stream, tmX, tmW, a, tiles_m, tiles_m * nb, (int)ntiles);
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
   }
   const bool deep = (long long)grid.x * grid.y <= (long long)num_sms * 3 / 2;
   if (BK == 64) {
-    if (deep) conv_gemm_tc_kernel<64, 1><<<grid, TTHREADS, Cfg<64, 1>::SMEM, stream>>>(tmX, tmW, a);
-    else conv_gemm_tc_kernel<64, 0><<<grid, TTHREADS, Cfg<64, 0>::SMEM, stream>>>(tmX, tmW, a);
+    if (deep) FQ3_LAUNCH((conv_gemm_tc_kernel<64, 1>), grid, TTHREADS, (Cfg<64, 1>::SMEM), stream, tmX, tmW, a);
+    else FQ3_LAUNCH((conv_gemm_tc_kernel<64, 0>), grid, TTHREADS, (Cfg<64, 0>::SMEM), stream, tmX, tmW, a);
   } else {
-    if (deep) conv_gemm_tc_kernel<32, 1><<<grid, TTHREADS, Cfg<32, 1>::SMEM, stream>>>(tmX, tmW, a);
-    else conv_gemm_tc_kernel<32, 0><<<grid, TTHREADS, Cfg<32, 0>::SMEM, stream>>>(tmX, tmW, a);
+    if (deep) FQ3_LAUNCH((conv_gemm_tc_kernel<32, 1>), grid, TTHREADS, (Cfg<32, 1>::SMEM), stream, tmX, tmW, a);
+    else FQ3_LAUNCH((conv_gemm_tc_kernel<32, 0>), grid, TTHREADS, (Cfg<32, 0>::SMEM), stream, tmX, tmW, a);
   }
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }

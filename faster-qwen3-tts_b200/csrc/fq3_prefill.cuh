@@ -19,6 +19,8 @@ __device__ __forceinline__ float rb(float x) { return __bfloat162float(__float2b
 __global__ void rmsnorm_rows_kernel(const __nv_bfloat16* __restrict__ X, const __nv_bfloat16* __restrict__ w, int H,
                                     float eps, __nv_bfloat16* __restrict__ Y) {
   __shared__ float red[8];
+  fq3gemm::pdl_launch();
+  fq3gemm::pdl_wait();
   const size_t row = blockIdx.x;
   const int tid = threadIdx.x;
   float v[8];
@@ -50,6 +52,8 @@ __global__ void rope_kv_kernel(__nv_bfloat16* __restrict__ QKV, int P, int nH, i
                                const __nv_bfloat16* kn, const float* __restrict__ cosT, const float* __restrict__ sinT,
                                int npos, int n_left_pad, float eps, __nv_bfloat16* __restrict__ kc,
                                __nv_bfloat16* __restrict__ vc, int S) {
+  fq3gemm::pdl_launch();
+  fq3gemm::pdl_wait();
   const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   const int nvec = nH + 2 * nKV;
   if (gw >= P * nvec) return;
@@ -99,6 +103,8 @@ __global__ void __launch_bounds__(256) attn_prefill_kernel(const __nv_bfloat16* 
                                                           const __nv_bfloat16* __restrict__ vc, int S, int n_left_pad,
                                                           __nv_bfloat16* __restrict__ OUT) {
   extern __shared__ float sm[];
+  fq3gemm::pdl_launch();
+  fq3gemm::pdl_wait();
   const int Ppad = (P + 31) & ~31;
   float* sc = sm;                 // [8][Ppad]
   float* qs = sm + 8 * Ppad;      // [8][128]
@@ -193,6 +199,8 @@ __global__ void __launch_bounds__(128) attn_prefill_mma_kernel(const __nv_bfloat
                                                               __nv_bfloat16* __restrict__ OUT) {
   constexpr int KT = 32;                                   // keys per staged tile
   __shared__ __align__(128) uint8_t sm[2][2][KT * 256];    // [buffer][K | V][key row x 256 B], 16-byte chunks XOR-swizzled
+  fq3gemm::pdl_launch();
+  fq3gemm::pdl_wait();
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int gq = lane >> 2, t = lane & 3;
   const int g = blockIdx.y, qb = blockIdx.x;
@@ -442,12 +450,12 @@ extern "C" int fq3_prefill(fq3_engine* e, int32_t slot, const void* embeds_dev, 
   const size_t attn_smem = (size_t)(8 * Ppad + 8 * 128) * sizeof(float);
   int rc;
   for (int l = 0; l < L; ++l) {
-    pf::rmsnorm_rows_kernel<<<P, 256, 0, stream>>>(x, (const bf*)k.t.ln_in + (size_t)l * H, H, T.rms_norm_eps, hn);
+    FQ3_LAUNCH((pf::rmsnorm_rows_kernel), P, 256, 0, stream, x, (const bf*)k.t.ln_in + (size_t)l * H, H, T.rms_norm_eps, hn);
     e->launches++;
     if ((rc = pf_gemm(e, hn, (const bf*)e->pf_qkv + (size_t)l * (qd + 2 * kd) * H, nullptr, wide, P, H, qd + 2 * kd, 0, stream))) return rc;
     {
       const int warps = P * (nH + 2 * nKV);
-      pf::rope_kv_kernel<<<(warps * 32 + 255) / 256, 256, 0, stream>>>(
+      FQ3_LAUNCH((pf::rope_kv_kernel), (warps * 32 + 255) / 256, 256, 0, stream, 
           wide, P, nH, nKV, (const bf*)k.t.qnorm + (size_t)l * 128, (const bf*)k.t.knorm + (size_t)l * 128, k.t.cos,
           k.t.sin, k.t.npos, n_left_pad, T.rms_norm_eps, (bf*)slot_tk(e, slot) + (size_t)l * nKV * S * 128,
           (bf*)slot_tv(e, slot) + (size_t)l * nKV * S * 128, S);
@@ -458,21 +466,21 @@ extern "C" int fq3_prefill(fq3_engine* e, int32_t slot, const void* embeds_dev, 
       const bf* vl = (const bf*)slot_tv(e, slot) + (size_t)l * nKV * S * 128;
       const int rep = nH / nKV;
       if (!g_fq3_scalar_prefill_attention && rep == 2)
-        pf::attn_prefill_mma_kernel<2><<<dim3((P + 31) / 32, nKV), 128, 0, stream>>>(wide, P, nH, nKV, kl, vl, S, n_left_pad, att);
+        FQ3_LAUNCH((pf::attn_prefill_mma_kernel<2>), dim3((P + 31) / 32, nKV), 128, 0, stream, wide, P, nH, nKV, kl, vl, S, n_left_pad, att);
       else if (!g_fq3_scalar_prefill_attention && rep == 1)
-        pf::attn_prefill_mma_kernel<1><<<dim3((P + 31) / 32, nKV), 128, 0, stream>>>(wide, P, nH, nKV, kl, vl, S, n_left_pad, att);
+        FQ3_LAUNCH((pf::attn_prefill_mma_kernel<1>), dim3((P + 31) / 32, nKV), 128, 0, stream, wide, P, nH, nKV, kl, vl, S, n_left_pad, att);
       else   // other GQA ratios (and FQ3_PREFILL_SCALAR_ATTN=1 for A/B runs): the scalar-FMA kernel of round 1
-        pf::attn_prefill_kernel<<<dim3((P + 7) / 8, nH), 256, attn_smem, stream>>>(wide, P, nH, nKV, kl, vl, S, n_left_pad, att);
+        FQ3_LAUNCH((pf::attn_prefill_kernel), dim3((P + 7) / 8, nH), 256, attn_smem, stream, wide, P, nH, nKV, kl, vl, S, n_left_pad, att);
     }
     e->launches++;
     if ((rc = pf_gemm(e, att, (const bf*)e->pf_o + (size_t)l * H * qd, x, x1, P, qd, H, 0, stream))) return rc;
-    pf::rmsnorm_rows_kernel<<<P, 256, 0, stream>>>(x1, (const bf*)k.t.ln_post + (size_t)l * H, H, T.rms_norm_eps, hn);
+    FQ3_LAUNCH((pf::rmsnorm_rows_kernel), P, 256, 0, stream, x1, (const bf*)k.t.ln_post + (size_t)l * H, H, T.rms_norm_eps, hn);
     e->launches++;
     if ((rc = pf_gemm(e, hn, (const bf*)e->pf_gu + (size_t)l * 2 * I * H, nullptr, wide, P, H, 2 * I, 1, stream))) return rc;
     if ((rc = pf_gemm(e, wide, (const bf*)e->pf_down + (size_t)l * H * I, x1, x, P, I, H, 0, stream))) return rc;
   }
   // final norm of the last row -> past_hidden; logits = codec_head(hidden)
-  pf::rmsnorm_rows_kernel<<<1, 256, 0, stream>>>(x + (size_t)(P - 1) * H, (const bf*)k.t.ln_f, H, T.rms_norm_eps, hn);
+  FQ3_LAUNCH((pf::rmsnorm_rows_kernel), 1, 256, 0, stream, x + (size_t)(P - 1) * H, (const bf*)k.t.ln_f, H, T.rms_norm_eps, hn);
   e->launches++;
   CK(cudaMemcpyAsync(hidden_out_dev, hn, (size_t)H * 2, cudaMemcpyDeviceToDevice, stream));
   if ((rc = pf_gemm(e, hn, (const bf*)e->pf_head, nullptr, (bf*)logits_out_dev, 1, H, T.vocab_size, 0, stream))) return rc;
