@@ -937,6 +937,16 @@ extern "C" void fq3_codec_stream_destroy(fq3_codec_stream* s) {
   delete s;
 }
 extern "C" int64_t fq3_codec_stream_frames(fq3_codec_stream* s) { return s ? s->frames : 0; }
+/* dst becomes a copy of src (state of every causal layer + position): a stream warmed once with a reference's frames
+ * serves as the template of every later request with that reference (3.8 MB device-to-device, stream-ordered) */
+extern "C" int fq3_codec_stream_copy(fq3_codec_stream* dst, fq3_codec_stream* src, void* stream_) {
+  if (!dst || !src || dst->owner != src->owner) return cfail(FQ3_ERR_INVALID, "streams of different codecs");
+  if (dst == src) return 0;
+  CodecDevGuard dev_guard(src->owner->dev);
+  CCK(cudaMemcpyAsync(dst->tails, src->tails, src->owner->tail_elems * 2, cudaMemcpyDeviceToDevice, (cudaStream_t)stream_));
+  dst->frames = src->frames;
+  return 0;
+}
 
 /* The next T code frames of n_streams streams (each with its own history) in one set of launches:
  * codes_dev int64 [n_streams][T][Q] -> pcm float32 [n_streams][T * total_upsample]; pcm_out_dev may be NULL (state

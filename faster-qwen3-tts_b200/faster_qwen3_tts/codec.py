@@ -230,6 +230,7 @@ class SpeechTokenizer:
         self._graphs = {}
         self._seen = {}
         self._stream_pool = []      # released stream handles: a request re-uses one (async reset) instead of cudaMalloc / cudaFree
+        self._ref_templates = {}    # content hash of a voice reference's codes -> stream warmed with them (bounded)
         self.native_front = (os.environ.get("FQ3_CODEC_TORCH_FRONT", "0") != "1") if native_front is None else native_front
         if backend == "engine":
             self._init_engine()
@@ -318,6 +319,9 @@ class SpeechTokenizer:
     def __del__(self):
         try:
             if self._h is not None:
+                for t in list(self._ref_templates.values()):
+                    t.close()
+                self._ref_templates = {}
                 for h in self._stream_pool:
                     self._lib.fq3_codec_stream_destroy(h)
                 self._stream_pool = []
@@ -422,6 +426,28 @@ class SpeechTokenizer:
         if self.backend != "engine" or not self.native_front:
             raise RuntimeError("stateful streaming needs the engine backend with the native front end")
         return CodecStream(self)
+
+    @torch.inference_mode()
+    def reference_stream(self, ref_codes: torch.Tensor) -> "CodecStream":
+        """A stream whose state is "these reference frames have been decoded": the first request with a reference warms
+        a template (one decode of the reference), every later one gets a device-to-device copy of it -- the codec-side
+        counterpart of the reference's voice-prompt cache (model.py:415-463)."""
+        import ctypes as C
+        import hashlib
+        rc = ref_codes.detach().to(torch.long).cpu().contiguous()
+        key = (tuple(rc.shape), hashlib.blake2b(rc.numpy().tobytes(), digest_size=16).digest())
+        tpl = self._ref_templates.get(key)
+        if tpl is None:
+            tpl = self.open_stream()
+            tpl.warm(ref_codes)
+            if len(self._ref_templates) >= 16:
+                self._ref_templates.pop(next(iter(self._ref_templates))).close()
+            self._ref_templates[key] = tpl
+        s = self.open_stream()
+        with torch.cuda.device(self._dev):
+            if self._lib.fq3_codec_stream_copy(s._h, tpl._h, C.c_void_p(torch.cuda.current_stream(self._dev).cuda_stream)):
+                raise RuntimeError(self._lib.fq3_codec_last_error().decode())
+        return s
 
     @torch.inference_mode()
     def push_streams(self, streams, codes: torch.Tensor, want_pcm: bool = True):

@@ -66,7 +66,7 @@ EXPORTS = [
     "fq3_codec_create", "fq3_codec_load_weights", "fq3_codec_decode", "fq3_codec_decode_batch", "fq3_codec_flops",
     "fq3_codec_load_frontend", "fq3_codec_decode_codes", "fq3_codec_frontend_flops",
     "fq3_codec_stream_create", "fq3_codec_stream_reset", "fq3_codec_stream_destroy", "fq3_codec_stream_frames",
-    "fq3_codec_stream_decode", "fq3_codec_launch_count",
+    "fq3_codec_stream_decode", "fq3_codec_stream_copy", "fq3_codec_launch_count",
     "fq3_codec_destroy", "fq3_codec_last_error",
 ]
 
@@ -143,6 +143,7 @@ def load_library() -> C.CDLL:
     lib.fq3_codec_stream_reset.argtypes = [C.c_void_p, C.c_void_p]
     lib.fq3_codec_stream_destroy.argtypes = [C.c_void_p]
     lib.fq3_codec_stream_destroy.restype = None
+    lib.fq3_codec_stream_copy.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     lib.fq3_codec_stream_frames.argtypes = [C.c_void_p]
     lib.fq3_codec_stream_frames.restype = C.c_int64
     lib.fq3_codec_stream_decode.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_int32, C.c_void_p, C.c_int32, C.c_void_p,

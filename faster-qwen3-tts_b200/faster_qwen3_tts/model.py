@@ -31,18 +31,33 @@ CONTEXT_FRAMES = 25  # model.py:1056
 
 class _StreamWindow:
     """Per-request state of the streaming codec-window policy (model.py:1052-1135), push-style so that several
-    requests of a batch can each keep their own window while their code chunks arrive interleaved."""
+    requests of a batch can each keep their own window while their code chunks arrive interleaved.
+
+    Phase 1 with an ICL reference is where the reference spends most of its codec time: every chunk re-decodes the
+    reference frames plus everything generated so far and keeps only the new tail.  The decoder is causal, so that tail
+    is exactly what a decoder STREAM that has already seen the reference produces for the new frames alone (bit for bit,
+    tests/test_gpu_codec.py).  When the tokenizer offers streams (engine codec) Phase 1 therefore runs on a copy of the
+    reference's warmed template stream (``SpeechTokenizer.reference_stream``): same samples, one chunk's worth of work,
+    and the reference itself is decoded once per voice instead of four times per request.  Phase 2 (25-frame context
+    windows without the reference) is the reference's approximation and is decoded exactly as the reference does.
+    ``FQ3_PHASE1_STREAM=0`` keeps the literal re-decode."""
 
     def __init__(self, owner, speech_tokenizer, ref_codes, chunk_size, to_host=True):
         self.st, self.ref_codes = speech_tokenizer, ref_codes
         self.min_cal = max(CONTEXT_FRAMES, chunk_size)
         self.all_codes, self.prev_len, self.spf = [], 0, None
         self.conv = owner._to_numpy if to_host else (lambda a: a.flatten())
+        self.p1 = None
+        if (ref_codes is not None and ref_codes.shape[0] > 0 and hasattr(speech_tokenizer, "reference_stream")
+                and getattr(speech_tokenizer, "native_front", False) and os.environ.get("FQ3_PHASE1_STREAM", "1") != "0"):
+            self.p1 = speech_tokenizer.reference_stream(ref_codes)
 
     def window(self, codec_chunk):
         """-> (codes [T,16] to decode, meta): the decode call the policy makes for this chunk"""
         self.all_codes.append(codec_chunk)
         n_new = codec_chunk.shape[0]
+        if self.spf is None and self.p1 is not None:
+            return codec_chunk, ("phase1_stream", sum(int(c.shape[0]) for c in self.all_codes), 0)
         flat = torch.cat(self.all_codes, dim=0)
         n_total = flat.shape[0]
         if self.spf is None:
@@ -57,6 +72,13 @@ class _StreamWindow:
         """decoded window -> the new samples of this chunk (trim of the reference / of the 25-frame context)"""
         audio = self.conv(audio)
         kind, a, b = meta
+        if kind == "phase1_stream":   # the stream produced exactly gen_audio[prev_len:] of the reference's Phase 1
+            self.prev_len += len(audio)
+            if a >= self.min_cal:
+                self.spf = self.prev_len / a
+                self.p1.close()
+                self.p1 = None
+            return audio
         if kind == "phase1":
             n_total, n_inp = a, b
             if self.ref_codes is not None:
@@ -74,6 +96,8 @@ class _StreamWindow:
 
     def push(self, codec_chunk):
         codes, meta = self.window(codec_chunk)
+        if meta[0] == "phase1_stream":
+            return self.finish(self.p1.push(codes), meta), self.st.sample_rate
         audio_list, sr = self.st.decode({"audio_codes": codes.unsqueeze(0)})
         return self.finish(audio_list[0], meta), sr
 
@@ -111,14 +135,18 @@ def decode_windows_batched(speech_tokenizer, wins, chunks):
                 out[i] = (wins[i].conv(a), speech_tokenizer.sample_rate)
         return out
     prepared = [w.window(c) for w, c in zip(wins, chunks)]
-    groups = {}
-    for i, (codes, _) in enumerate(prepared):
-        groups.setdefault(int(codes.shape[0]), []).append(i)
+    groups, sgroups = {}, {}
+    for i, (codes, meta) in enumerate(prepared):
+        (sgroups if meta[0] == "phase1_stream" else groups).setdefault(int(codes.shape[0]), []).append(i)
     out = [None] * len(wins)
     sr = speech_tokenizer.sample_rate if hasattr(speech_tokenizer, "sample_rate") else 24000
     for T, idxs in groups.items():
         audio_list, sr = speech_tokenizer.decode({"audio_codes": torch.stack([prepared[i][0] for i in idxs])})
         for i, a in zip(idxs, audio_list):
+            out[i] = (wins[i].finish(a, prepared[i][1]), sr)
+    for n, idxs in sgroups.items():   # Phase-1 rows riding on reference-warmed streams: one call for all of them
+        pcm = speech_tokenizer.push_streams([wins[i].p1 for i in idxs], torch.stack([prepared[i][0] for i in idxs]))
+        for i, a in zip(idxs, pcm):
             out[i] = (wins[i].finish(a, prepared[i][1]), sr)
     return out
 

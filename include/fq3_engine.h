@@ -230,6 +230,9 @@ int fq3_codec_stream_create(fq3_codec* c, fq3_codec_stream** out);
 int fq3_codec_stream_reset(fq3_codec_stream* s, void* stream);
 void fq3_codec_stream_destroy(fq3_codec_stream* s);
 int64_t fq3_codec_stream_frames(fq3_codec_stream* s);
+/* dst := src (layer histories + position), stream-ordered device copy: a stream warmed once with a voice reference is
+ * the template of every later request that uses that reference */
+int fq3_codec_stream_copy(fq3_codec_stream* dst, fq3_codec_stream* src, void* stream);
 int fq3_codec_stream_decode(fq3_codec* c, fq3_codec_stream* const* streams, int32_t n_streams, const int64_t* codes_dev,
                             int32_t T, float* pcm_out_dev, void* stream);
 double fq3_codec_flops(fq3_codec* c, int32_t T4);

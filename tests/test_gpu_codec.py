@@ -201,3 +201,30 @@ def test_stateful_window_policy_streams_the_non_streaming_audio(full_codec):
     assert [p.shape[0] for p in parts] == [c.shape[0] * 1920 for c in chunks]
     whole, _ = st.decode({"audio_codes": torch.cat([ref] + chunks)[None]})
     assert torch.equal(torch.cat(parts), whole[0][174 * 1920:])
+
+
+def test_phase1_on_reference_stream_is_sample_identical_to_the_literal_window_policy(full_codec, monkeypatch):
+    """The default window policy runs Phase 1 of an ICL request on a copy of the reference's warmed template stream instead
+    of re-decoding [reference + everything so far] per chunk (model.py:1085-1112): every chunk must be bit-identical to the
+    literal re-decode (FQ3_PHASE1_STREAM=0), Phase 2 included, for two requests sharing one cached reference."""
+    from faster_qwen3_tts.model import _StreamWindow
+    import types
+    st = full_codec
+    g = torch.Generator().manual_seed(31)
+    ref = torch.randint(0, 2048, (174, 16), generator=g)          # host tensor, like the cached voice prompt holds it
+    owner = types.SimpleNamespace(_to_numpy=None)
+    for req in range(2):
+        chunks = [torch.randint(0, 2048, (8, 16), generator=g).cuda() for _ in range(6)] + [torch.randint(0, 2048, (5, 16), generator=g).cuda()]
+        monkeypatch.setenv("FQ3_PHASE1_STREAM", "0")
+        lit = _StreamWindow(owner, st, ref, 8, to_host=False)
+        assert lit.p1 is None
+        monkeypatch.setenv("FQ3_PHASE1_STREAM", "1")
+        fast = _StreamWindow(owner, st, ref, 8, to_host=False)
+        assert fast.p1 is not None and fast.p1.frames == 174
+        for ci, c in enumerate(chunks):
+            a, _ = lit.push(c)
+            b, _ = fast.push(c)
+            assert a.shape == b.shape == (c.shape[0] * 1920,), (req, ci)
+            assert torch.equal(a, b), (req, ci)
+        assert fast.p1 is None and fast.spf == lit.spf == 1920.0
+    assert len(st._ref_templates) == 1        # one warmed template served both requests

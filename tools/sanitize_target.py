@@ -63,6 +63,15 @@ if which in ("all", "codec"):
     pcm, sr = st.decode({"audio_codes": codes})
     torch.cuda.synchronize()
     print("OK codec", tuple(pcm[0].shape), sr, flush=True)
+    # stateful streams: history rows in front of every causal layer, two streams at different positions in one call
+    s1, s2 = st.open_stream(), st.open_stream()
+    s1.warm(codes[0, :5])
+    a = s1.push(codes[0, 5:])
+    b = st.push_streams([s1, s2], torch.stack([codes[1, :3], codes[1, :3]]))
+    torch.cuda.synchronize()
+    whole, _ = st.decode({"audio_codes": codes[:1]})
+    print("OK codec streams", tuple(a.shape), [tuple(x.shape) for x in b], "tail equals one-shot:",
+          bool(torch.equal(a, whole[0][5 * 1920:])), flush=True)
 if which in ("all", "prefill"):
     p = Pair(cfg, seed=3, dtype=torch.bfloat16, max_seq_len=64)
     if p.engine.has_prefill:
@@ -70,5 +79,9 @@ if which in ("all", "prefill"):
         lg, hid = p.engine.prefill(tie.cuda(), n_left_pad=3)
         torch.cuda.synchronize()
         print("OK prefill", tuple(lg.shape), flush=True)
+        tie, _, _ = O.make_inputs(cfg, 50, 1, seed=1, dtype=torch.bfloat16)   # two query blocks, two key tiles
+        lg, hid = p.engine.prefill(tie.cuda(), n_left_pad=0)
+        torch.cuda.synchronize()
+        print("OK prefill P=50", tuple(lg.shape), bool(torch.isfinite(lg.float()).all()), flush=True)
     else:
         print("prefill weights not set for this geometry", flush=True)
