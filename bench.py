@@ -212,7 +212,10 @@ def workload_config(args, P=None, **extra):
                      f"({args.ref_frames} reference frames), {args.frames} frames, chunk_size={args.chunk}, "
                      f"T=0.9 top_k=50 top_p=1.0 penalty=1.05, min_new_tokens=max_new_tokens (fixed work)",
          "batch_per_gpu": 1, "parallelism": f"replicas x{args.gpus} (no collective)",
-         "l2_policy": "per-step weight stream (3.2 GB tape) exceeds the 126 MB L2; no explicit flush needed"}
+         "l2_policy": "per-step weight stream (3.2 GB tape) exceeds the 126 MB L2; no explicit flush needed",
+         "codec_policy": "reference window policy (model.py:1052-1135), sample-identical; Phase 1 of a request with an ICL "
+                         "reference runs on a copy of that reference's warmed decoder stream (cached per voice like the voice "
+                         "prompt; the e2e leg clears both caches every step, so it pays the reference decode each time)"}
     c.update(extra)
     return c
 
@@ -357,7 +360,9 @@ def run_b200(args):
     e_frames = h2d = d2h = 0
     e_ttfa = []
     for _ in range(args.steps):
-        model._voice_prompt_cache.clear()   # every step pays the voice-clone prompt, like a new speaker
+        model._voice_prompt_cache.clear()   # every step pays the voice-clone prompt, like a new speaker ...
+        if hasattr(model.model.model.speech_tokenizer, "clear_reference_cache"):
+            model.model.model.speech_tokenizer.clear_reference_cache()   # ... and the codec-side warm-up of its reference
         n, a, b, tf = step_e2e()
         e_frames += n
         h2d, d2h = a, b

@@ -420,12 +420,23 @@ class SpeechTokenizer:
         return [pcm[b] for b in range(B)], self.sample_rate
 
     # ---- stateful streaming (fq3_codec_stream_*) -----------------------------------------------------------
+    @property
+    def supports_streams(self) -> bool:
+        """decoder streams exist only on the engine codec with the native front end"""
+        return self.backend == "engine" and self.native_front and self._h is not None
+
     def open_stream(self) -> "CodecStream":
         """A decoder stream that keeps every causal layer's history on the device: ``push(codes[n,16])`` returns the
         1920*n samples of exactly those frames, at the cost of n frames (no window re-decode)."""
-        if self.backend != "engine" or not self.native_front:
+        if not self.supports_streams:
             raise RuntimeError("stateful streaming needs the engine backend with the native front end")
         return CodecStream(self)
+
+    def clear_reference_cache(self) -> None:
+        """forget the warmed template streams (a new speaker pays one decode of its reference again)"""
+        for t in list(self._ref_templates.values()):
+            t.close()
+        self._ref_templates = {}
 
     @torch.inference_mode()
     def reference_stream(self, ref_codes: torch.Tensor) -> "CodecStream":

@@ -48,8 +48,8 @@ class _StreamWindow:
         self.all_codes, self.prev_len, self.spf = [], 0, None
         self.conv = owner._to_numpy if to_host else (lambda a: a.flatten())
         self.p1 = None
-        if (ref_codes is not None and ref_codes.shape[0] > 0 and hasattr(speech_tokenizer, "reference_stream")
-                and getattr(speech_tokenizer, "native_front", False) and os.environ.get("FQ3_PHASE1_STREAM", "1") != "0"):
+        if (ref_codes is not None and ref_codes.shape[0] > 0 and getattr(speech_tokenizer, "supports_streams", False)
+                and os.environ.get("FQ3_PHASE1_STREAM", "1") != "0"):
             self.p1 = speech_tokenizer.reference_stream(ref_codes)
 
     def window(self, codec_chunk):
@@ -488,7 +488,7 @@ class FasterQwen3TTS:
             yield new_audio, sr, timing
 
     def _make_window(self, speech_tokenizer, ref_codes, chunk_size, to_host=True):
-        if self.streaming_codec == "stateful" and hasattr(speech_tokenizer, "open_stream"):
+        if self.streaming_codec == "stateful" and getattr(speech_tokenizer, "supports_streams", False):
             return _StatefulWindow(self, speech_tokenizer, ref_codes, chunk_size, to_host)
         if self.streaming_codec not in ("window", "stateful"):
             raise ValueError("streaming_codec must be 'window' or 'stateful'")

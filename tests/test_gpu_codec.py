@@ -213,6 +213,7 @@ def test_phase1_on_reference_stream_is_sample_identical_to_the_literal_window_po
     g = torch.Generator().manual_seed(31)
     ref = torch.randint(0, 2048, (174, 16), generator=g)          # host tensor, like the cached voice prompt holds it
     owner = types.SimpleNamespace(_to_numpy=None)
+    st.clear_reference_cache()
     for req in range(2):
         chunks = [torch.randint(0, 2048, (8, 16), generator=g).cuda() for _ in range(6)] + [torch.randint(0, 2048, (5, 16), generator=g).cuda()]
         monkeypatch.setenv("FQ3_PHASE1_STREAM", "0")

@@ -26,6 +26,7 @@ class FakeStream:
 class FakeTokenizer:
     """decode(): 1920 samples per frame whose value is the frame's first code; streams: the same, frame by frame"""
     sample_rate = 24000
+    supports_streams = True
 
     def __init__(self):
         self.calls = []
