@@ -77,6 +77,9 @@ def main():
     ap.add_argument("--language", default=os.environ.get("QWEN_TTS_LANGUAGE", "Auto"))
     ap.add_argument("--max-batch", type=int, default=16)
     ap.add_argument("--chunk-size", type=int, default=8)
+    ap.add_argument("--streaming-codec", default="window", choices=["window", "stateful"],
+                    help="window: the reference's two-phase window policy (sample-exact); stateful: one decoder stream per "
+                         "request, a third of the codec work under load, audio = the non-streaming decode")
     ap.add_argument("--host", default="0.0.0.0")
     ap.add_argument("--port", type=int, default=8000)
     ap.add_argument("--device", default="cuda")
@@ -89,7 +92,8 @@ def main():
         model = FasterQwen3TTS.from_synthetic(args.model.split(":", 1)[1], device=args.device, dtype=torch.bfloat16,
                                               max_batch=args.max_batch)
     else:
-        model = FasterQwen3TTS.from_pretrained(args.model, device=args.device)
+        model = FasterQwen3TTS.from_pretrained(args.model, device=args.device, max_batch=args.max_batch)
+    model.streaming_codec = args.streaming_codec
     if args.voices:
         voices = json.load(open(args.voices))
         default = next(iter(voices))

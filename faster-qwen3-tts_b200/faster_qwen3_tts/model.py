@@ -213,7 +213,9 @@ class FasterQwen3TTS:
                         attn_implementation: str = "sdpa", max_seq_len: int = 2048, backend: str = "torch",
                         quant: str = "BF16", gguf_talker_path=None, gguf_codec_path=None, qwentts_library_path=None,
                         qwentts_use_fa: bool = True, qwentts_clamp_fp16: bool = False, qwentts_ref_cache_dir=None,
-                        cache_dir=None, local_files_only: bool = False):
+                        cache_dir=None, local_files_only: bool = False, max_batch: int = 1):
+        """Same arguments as the reference (model.py:106-124); ``max_batch`` (trailing, engine-specific) = request slots
+        of the engine: > 1 enables the batched persistent kernel / continuous batching (serving.py)."""
         if backend not in ("torch", "ggml", "qwentts"):
             raise ValueError(f"Unsupported backend {backend!r}. Expected 'torch', 'ggml', or 'qwentts'.")
         if backend in ("ggml", "qwentts"):
@@ -224,7 +226,8 @@ class FasterQwen3TTS:
         if not device.startswith("cuda") or not torch.cuda.is_available():
             raise ValueError("CUDA graphs require CUDA device")
         if str(model_name).startswith("synthetic:"):
-            return cls.from_synthetic(str(model_name).split(":", 1)[1], device=device, dtype=dtype, max_seq_len=max_seq_len)
+            return cls.from_synthetic(str(model_name).split(":", 1)[1], device=device, dtype=dtype, max_seq_len=max_seq_len,
+                                      max_batch=max_batch)
         try:
             from qwen_tts import Qwen3TTSModel
         except ImportError as ex:
@@ -232,7 +235,7 @@ class FasterQwen3TTS:
                               "for random-init weights of the real geometry") from ex
         base = Qwen3TTSModel.from_pretrained(model_name, device_map=device, torch_dtype=dtype,
                                              attn_implementation=attn_implementation)
-        return cls._wrap(base, device, dtype, max_seq_len)
+        return cls._wrap(base, device, dtype, max_seq_len, max_batch=max_batch)
 
     @classmethod
     def _wrap(cls, base_model, device, dtype, max_seq_len, num_ctas: int = 0, max_batch: int = 1):
