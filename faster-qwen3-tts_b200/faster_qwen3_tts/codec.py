@@ -20,7 +20,7 @@ from __future__ import annotations
 
 import math
 from dataclasses import dataclass, field
-from typing import List, Tuple
+from typing import List, Optional, Tuple
 
 import torch
 import torch.nn as nn
@@ -439,15 +439,18 @@ class SpeechTokenizer:
         self._ref_templates = {}
 
     @torch.inference_mode()
-    def reference_stream(self, ref_codes: torch.Tensor) -> "CodecStream":
+    def reference_stream(self, ref_codes: torch.Tensor, create: bool = True) -> Optional["CodecStream"]:
         """A stream whose state is "these reference frames have been decoded": the first request with a reference warms
         a template (one decode of the reference), every later one gets a device-to-device copy of it -- the codec-side
-        counterpart of the reference's voice-prompt cache (model.py:415-463)."""
+        counterpart of the reference's voice-prompt cache (model.py:415-463).  ``create=False``: None when no template
+        exists for this reference yet (the caller decides when to pay for the warm-up)."""
         import ctypes as C
         import hashlib
         rc = ref_codes.detach().to(torch.long).cpu().contiguous()
         key = (tuple(rc.shape), hashlib.blake2b(rc.numpy().tobytes(), digest_size=16).digest())
         tpl = self._ref_templates.get(key)
+        if tpl is None and not create:
+            return None
         if tpl is None:
             tpl = self.open_stream()
             tpl.warm(ref_codes)

@@ -47,15 +47,23 @@ class _StreamWindow:
         self.min_cal = max(CONTEXT_FRAMES, chunk_size)
         self.all_codes, self.prev_len, self.spf = [], 0, None
         self.conv = owner._to_numpy if to_host else (lambda a: a.flatten())
-        self.p1 = None
+        self.p1, self._p1_pending = None, False
         if (ref_codes is not None and ref_codes.shape[0] > 0 and getattr(speech_tokenizer, "supports_streams", False)
                 and os.environ.get("FQ3_PHASE1_STREAM", "1") != "0"):
-            self.p1 = speech_tokenizer.reference_stream(ref_codes)
+            # known voice: a copy of its warmed template, ready before the first chunk.  New voice: the FIRST chunk takes the
+            # literal re-decode (one decode of reference + 8 frames -- nothing cheaper exists for the first audio), the
+            # template is warmed when the second chunk arrives, i.e. off the time-to-first-audio path.
+            self.p1 = speech_tokenizer.reference_stream(ref_codes, create=False)
+            self._p1_pending = self.p1 is None
 
     def window(self, codec_chunk):
         """-> (codes [T,16] to decode, meta): the decode call the policy makes for this chunk"""
         self.all_codes.append(codec_chunk)
         n_new = codec_chunk.shape[0]
+        if self._p1_pending and self.spf is None and len(self.all_codes) > 1:
+            self._p1_pending = False
+            self.p1 = self.st.reference_stream(self.ref_codes)            # warms and caches the voice's template
+            self.p1.warm(torch.cat(self.all_codes[:-1], dim=0))           # catch up on the frames already played
         if self.spf is None and self.p1 is not None:
             return codec_chunk, ("phase1_stream", sum(int(c.shape[0]) for c in self.all_codes), 0)
         flat = torch.cat(self.all_codes, dim=0)

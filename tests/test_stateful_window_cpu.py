@@ -17,6 +17,9 @@ class FakeStream:
     def push(self, codes):
         return self.st.push_streams([self], codes[None])[0]
 
+    def close(self):
+        pass
+
     def warm(self, codes):
         self.st.calls.append(("warm", int(codes.shape[0])))
         self.warmed += int(codes.shape[0])
@@ -87,3 +90,51 @@ def test_batched_stateful_windows_group_by_new_frames_and_keep_row_order():
     assert sorted(st.calls) == [("push", 1, 3), ("push", 3, 8)]
     for (audio, sr), c in zip(res, chunks):
         assert sr == 24000 and audio.shape[0] == c.shape[0] * 1920 and float(audio[0]) == float(c[0, 0])
+
+
+class FakeTokenizerWithTemplates(FakeTokenizer):
+    """adds the per-voice template cache of SpeechTokenizer.reference_stream"""
+
+    def __init__(self):
+        super().__init__()
+        self.templates = {}
+
+    def reference_stream(self, ref_codes, create=True):
+        key = tuple(int(x) for x in ref_codes[:, 0])
+        if key not in self.templates:
+            if not create:
+                return None
+            self.calls.append(("template_warm", len(key)))
+            self.templates[key] = True
+        s = FakeStream(self)
+        s.frames = len(key)
+        self.calls.append(("template_copy",))
+        return s
+
+
+def test_window_policy_phase1_new_voice_is_literal_first_then_streams_known_voice_streams_at_once(monkeypatch):
+    """default ("window") policy with an ICL reference: a voice never seen takes the literal re-decode for its FIRST chunk
+    (time to first audio) and warms its template when the second chunk arrives; a known voice streams from chunk one;
+    Phase 2 is the reference's 25-frame window either way; the audio is the same as the literal policy's."""
+    monkeypatch.delenv("FQ3_PHASE1_STREAM", raising=False)
+    st = FakeTokenizerWithTemplates()
+    ref = torch.arange(100, 110)[:, None].expand(10, 16)
+    chunks = [torch.full((8, 16), v) for v in (1, 2, 3, 4, 5)]
+    o = _owner("window")
+
+    def run(tok):
+        tok.calls.clear()
+        return [a for a, _, _ in FasterQwen3TTS._stream_audio(o, ((c, {}) for c in chunks), tok, ref, 8, to_host=False)]
+
+    new_voice = run(st)
+    kinds = [c[0] for c in st.calls]
+    assert kinds == ["decode", "template_warm", "template_copy", "warm", "push", "push", "push", "decode"], st.calls
+    assert st.calls[0] == ("decode", (1, 18, 16)) and st.calls[3] == ("warm", 8)      # reference + 8 frames; catch-up of chunk 1
+    assert st.calls[-1] == ("decode", (1, 33, 16))                                      # Phase 2: 25 context + 8 new
+    known_voice = run(st)
+    assert [c[0] for c in st.calls] == ["template_copy", "push", "push", "push", "push", "decode"], st.calls
+    monkeypatch.setenv("FQ3_PHASE1_STREAM", "0")
+    literal = run(st)
+    assert [c[0] for c in st.calls] == ["decode"] * 5 and [c[1][1] for c in st.calls] == [18, 26, 34, 42, 33]
+    for a, b, c in zip(new_voice, known_voice, literal):
+        assert a.shape[0] == 8 * 1920 and torch.equal(a, b) and torch.equal(a, c)
