@@ -210,10 +210,39 @@ class FasterQwen3TTS:
 
     @staticmethod
     def _reject_ggml_cached_reference_args(ref_spk, ref_rvq, ref_spk_emb, ref_codes) -> None:
-        if any(v is not None for v in (ref_spk, ref_rvq, ref_spk_emb, ref_codes)):
+        """``.spk`` / ``.rvq`` FILES are qwentts.cpp's own on-disk formats (read by qwentts-cpp-python,
+        ggml_backend.py:476-509): like the reference's torch backend they are refused here with the reference's message
+        (tests/test_voice_clone_prompt_api.py:116-134).  The DECODED form of such a cached reference -- ``ref_spk_emb`` (the
+        speaker vector) and ``ref_codes`` (the reference's codec frames) as arrays -- is accepted, see
+        ``_cached_reference_prompt``."""
+        if any(v is not None for v in (ref_spk, ref_rvq)):
             raise NotImplementedError(
                 "ref_spk/ref_rvq cached qwentts.cpp references require backend='ggml'. "
                 "Use voice_clone_prompt for precomputed prompts with the torch backend.")
+
+    def _cached_reference_prompt(self, ref_spk_emb, ref_codes, voice_clone_prompt):
+        """SURVEY 8(f) item 4, in-memory half: a cached reference in decoded form -> the voice_clone_prompt dict the prompt
+        builder consumes (what ggml_backend.py:476-509 hands to qwentts.cpp).  ref_spk_emb: [H_talker] floats; ref_codes:
+        None (x-vector cloning) or int array [T,16] of reference codec frames (ICL cloning, needs ref_text)."""
+        if ref_spk_emb is None and ref_codes is None:
+            return voice_clone_prompt
+        if voice_clone_prompt is not None:
+            raise ValueError("pass either voice_clone_prompt or ref_spk_emb/ref_codes, not both")
+        if ref_spk_emb is None:
+            raise ValueError("ref_spk/ref_spk_emb is required for cached voice cloning.")
+        emb = torch.as_tensor(np.ascontiguousarray(np.asarray(ref_spk_emb, dtype=np.float32)).reshape(-1))
+        if emb.numel() == 0:
+            raise ValueError("ref_spk_emb must not be empty.")
+        H = self.model.model.config.talker_config.hidden_size
+        if emb.numel() != H:
+            raise ValueError(f"ref_spk_emb has {emb.numel()} values, the talker expects {H}")
+        codes = None
+        if ref_codes is not None:
+            codes = torch.as_tensor(np.ascontiguousarray(np.asarray(ref_codes, dtype=np.int64)))
+            ng = self.model.model.config.talker_config.num_code_groups
+            if codes.dim() != 2 or codes.shape[1] != ng or codes.shape[0] == 0:
+                raise ValueError(f"ref_codes must be a non-empty [T, {ng}] array of codec frames")
+        return dict(ref_spk_embedding=[emb], ref_code=[codes], x_vector_only_mode=[codes is None], icl_mode=[codes is not None])
 
     # ------------------------------------------------------------------ construction
     @classmethod
@@ -607,6 +636,7 @@ class FasterQwen3TTS:
                              instruct: Optional[str] = None, ref_spk=None, ref_rvq=None, ref_spk_emb=None,
                              ref_codes=None, voice_clone_prompt=None) -> Tuple[list, int]:
         self._reject_ggml_cached_reference_args(ref_spk, ref_rvq, ref_spk_emb, ref_codes)
+        voice_clone_prompt = self._cached_reference_prompt(ref_spk_emb, ref_codes, voice_clone_prompt)
         from .generate import fast_generate
         nsm = self._resolve_non_streaming_mode(non_streaming_mode, default=False)
         m, talker, config, tie, tam, tth, tpe, ref_codes = self._prepare_generation(
@@ -635,6 +665,7 @@ class FasterQwen3TTS:
                                        ref_codes=None, voice_clone_prompt=None
                                        ) -> Generator[Tuple[np.ndarray, int, dict], None, None]:
         self._reject_ggml_cached_reference_args(ref_spk, ref_rvq, ref_spk_emb, ref_codes)
+        voice_clone_prompt = self._cached_reference_prompt(ref_spk_emb, ref_codes, voice_clone_prompt)
         nsm = self._resolve_non_streaming_mode(non_streaming_mode, default=False)
         m, talker, config, tie, tam, tth, tpe, ref_codes = self._prepare_generation(
             text=text, language=language, ref_audio=ref_audio, ref_text=ref_text, xvec_only=xvec_only,

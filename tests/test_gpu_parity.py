@@ -328,6 +328,19 @@ def test_public_api_end_to_end_tiny():
     assert a[0].shape[0] == 9 * 1920
     with pytest.raises(ValueError, match="ref_audio is required"):
         m.generate_voice_clone("x", "English")
+    # a cached reference in decoded form: speaker vector alone = x-vector cloning, with the
+    # reference's codec frames = ICL cloning (frames are acoustic context of the codec and trimmed from the output)
+    H = m.model.model.config.talker_config.hidden_size
+    g = np.random.default_rng(0)
+    spk = g.standard_normal(H).astype(np.float32) * 0.1
+    a, sr = m.generate_voice_clone("cached voice", "English", ref_spk_emb=spk, max_new_tokens=8, min_new_tokens=8)
+    assert a[0].shape[0] == 8 * 1920 and np.isfinite(a[0]).all()
+    codes = g.integers(0, 200, size=(20, 16)).astype(np.int32)
+    chunks = list(m.generate_voice_clone_streaming("cached voice", "English", ref_text="the reference words", ref_spk_emb=spk,
+                                                   ref_codes=codes, max_new_tokens=16, min_new_tokens=16, chunk_size=8))
+    assert [c[0].shape[0] for c in chunks] == [8 * 1920, 8 * 1920]
+    with pytest.raises(ValueError, match="ref_text is required"):
+        m.generate_voice_clone("cached voice", "English", ref_spk_emb=spk, ref_codes=codes, max_new_tokens=4)
 
 
 @pytest.mark.gpu

@@ -92,3 +92,38 @@ def test_streaming_window_policy_matches_reference_arithmetic():
         assert got.shape[0] == 70 * 1920
         assert np.array_equal(got[::1920], np.arange(70, dtype=np.float32))
         assert all(sr == 24000 for _, sr, _ in out)
+
+
+def _cfg_model(H=8, ng=16):
+    tc = types.SimpleNamespace(hidden_size=H, num_code_groups=ng)
+    return _m(types.SimpleNamespace(model=types.SimpleNamespace(config=types.SimpleNamespace(talker_config=tc))))
+
+
+def test_cached_reference_files_refused_like_the_reference_arrays_accepted():
+    """.spk / .rvq PATHS (qwentts.cpp's formats) -> the reference's NotImplementedError (its own unit test,
+    tests/test_voice_clone_prompt_api.py:116-134); the decoded form (speaker vector + codec frames as arrays) becomes the
+    voice_clone_prompt dict of the prompt builder (in-memory half)."""
+    m = _cfg_model()
+    with pytest.raises(NotImplementedError, match="backend='ggml'"):
+        m.generate_voice_clone(text="hello", language="English", ref_spk="speaker.spk")
+    with pytest.raises(NotImplementedError, match="backend='ggml'"):
+        next(m.generate_voice_clone_streaming(text="hello", language="English", ref_rvq="speaker.rvq"))
+    assert m._cached_reference_prompt(None, None, {"x": 1}) == {"x": 1}
+    emb = np.arange(8, dtype=np.float64)
+    xv = m._cached_reference_prompt(emb, None, None)
+    assert xv["x_vector_only_mode"] == [True] and xv["icl_mode"] == [False] and xv["ref_code"] == [None]
+    assert xv["ref_spk_embedding"][0].dtype == torch.float32 and xv["ref_spk_embedding"][0].tolist() == emb.tolist()
+    codes = np.arange(3 * 16, dtype=np.int32).reshape(3, 16)
+    icl = m._cached_reference_prompt(emb, codes, None)
+    assert icl["icl_mode"] == [True] and icl["x_vector_only_mode"] == [False]
+    assert icl["ref_code"][0].dtype == torch.long and icl["ref_code"][0].shape == (3, 16)
+    with pytest.raises(ValueError, match="ref_spk/ref_spk_emb is required"):
+        m._cached_reference_prompt(None, codes, None)
+    with pytest.raises(ValueError, match="must not be empty"):
+        m._cached_reference_prompt(np.zeros(0), None, None)
+    with pytest.raises(ValueError, match="the talker expects 8"):
+        m._cached_reference_prompt(np.zeros(5), None, None)
+    with pytest.raises(ValueError, match=r"\[T, 16\]"):
+        m._cached_reference_prompt(emb, np.zeros((3, 4)), None)
+    with pytest.raises(ValueError, match="not both"):
+        m._cached_reference_prompt(emb, None, {"ref_spk_embedding": [emb]})
