@@ -1321,6 +1321,55 @@ __device__ __forceinline__ float xs_get(Ctx& c, int idx) {
 // ------------------------------------------------------------------------------------------------------------
 // NT == 2 is the predictor prefill (slot0 == 0: no cached keys at all); NT == 1 the single-token passes.
 // Register budget is 168/thread (9 warps per SM), so K rows and V rows are fetched in two round trips.
+// ------------------------------------------------------------------------------------------------------------
+// Warp reduce-scatter of 34 per-lane partial sums (2 heads x 17 keys of the predictor attention): instead of a 5-round
+// butterfly on every value (170 shuffles, every lane ends with every sum), each round halves the value set -- a lane
+// keeps one half and hands the other to its partner -- so 36 shuffles leave every sum on exactly one lane.  The owner's
+// value is bit-identical to the butterfly's (same pairing tree, fp32 addition commutes).  own_lane / own_slot: where
+// the sum of original index idx ends up.
+// ------------------------------------------------------------------------------------------------------------
+template <int N, int O>
+__device__ __forceinline__ void rs_step(float* a, int lane) {
+  constexpr int HH = (N + 1) / 2;
+  const bool up = (lane & O) != 0;
+#pragma unroll
+  for (int i = 0; i < HH; ++i) {
+    const float lo = a[i];
+    const float hi = (i + HH < N) ? a[i + HH] : 0.f;
+    const float send = up ? lo : hi, keep = up ? hi : lo;
+    a[i] = keep + __shfl_xor_sync(0xffffffffu, send, O);
+  }
+}
+__host__ __device__ constexpr int rs34_lane(int idx) {
+  int l = 0, r = idx;
+  if (r >= 17) { l |= 16; r -= 17; }
+  if (r >= 9) { l |= 8; r -= 9; }
+  if (r >= 5) { l |= 4; r -= 5; }
+  if (r >= 3) { l |= 2; r -= 3; }
+  if (r >= 2) { l |= 1; r -= 2; }
+  return l;
+}
+__host__ __device__ constexpr int rs34_slot(int idx) {
+  int r = idx;
+  if (r >= 17) r -= 17;
+  if (r >= 9) r -= 9;
+  if (r >= 5) r -= 5;
+  if (r >= 3) r -= 3;
+  if (r >= 2) r -= 2;
+  return r;
+}
+// scores sc[2][1][17] (per-lane partials) -> mine[hh] = the full dot product of key `lane` (lanes >= 17: untouched)
+template <int HHI = 0, int J = 0>
+__device__ __forceinline__ void rs34_gather(const float* a, int lane, float* mine) {
+  if constexpr (HHI < 2) {
+    constexpr int idx = HHI * 17 + J;
+    const float v = __shfl_sync(0xffffffffu, a[rs34_slot(idx)], rs34_lane(idx));
+    if (lane == J) mine[HHI] = v;
+    if constexpr (J + 1 < 17) rs34_gather<HHI, J + 1>(a, lane, mine);
+    else rs34_gather<HHI + 1, 0>(a, lane, mine);
+  }
+}
+
 template <bool BF>
 struct SmallKV {  // cached K/V rows of this warp's kv group, fetched in the shadow of the QKV barrier
   using Raw = typename std::conditional<BF, uint2, float4>::type;
@@ -1460,14 +1509,29 @@ __device__ void attention_small_all(Ctx& c, const StackDev& S, int layer, int sl
           sc[hh][t][j] = d;
         }
     }
-#pragma unroll
-    for (int o = 16; o; o >>= 1)
+    float dotk[2] = {0.f, 0.f};   // NT == 1: the full q.k of key `lane` for the two heads (reduce-scatter path)
+    if constexpr (NT == 1) {
+      float a[34];
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh)
 #pragma unroll
-        for (int t = 0; t < NT; ++t)
+        for (int j = 0; j < 17; ++j) a[hh * 17 + j] = sc[hh][0][j];
+      rs_step<34, 16>(a, c.lane);
+      rs_step<17, 8>(a, c.lane);
+      rs_step<9, 4>(a, c.lane);
+      rs_step<5, 2>(a, c.lane);
+      rs_step<3, 1>(a, c.lane);
+      rs34_gather(a, c.lane, dotk);
+    } else {
 #pragma unroll
-          for (int j = 0; j < MAXK; ++j) sc[hh][t][j] += __shfl_xor_sync(0xffffffffu, sc[hh][t][j], o);
+      for (int o = 16; o; o >>= 1)
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh)
+#pragma unroll
+          for (int t = 0; t < NT; ++t)
+#pragma unroll
+            for (int j = 0; j < MAXK; ++j) sc[hh][t][j] += __shfl_xor_sync(0xffffffffu, sc[hh][t][j], o);
+    }
     // ---- round trip 2: cached V rows (issued before the softmax arithmetic so the latency overlaps it)
     Raw vraw[NOLD];
 #pragma unroll
@@ -1476,19 +1540,26 @@ __device__ void attention_small_all(Ctx& c, const StackDev& S, int layer, int sl
       else if (j < slot0) vraw[j] = __ldcg(reinterpret_cast<const Raw*>(vb + (size_t)j * 128 * esz) + c.lane);
       else zero_raw(vraw[j]);
     }
-    // softmax with the keys distributed over lanes: every lane knows all scores (max is redundant and cheap), but
-    // only lane j exponentiates key j; the sum is a warp reduction and p_j is broadcast with one shuffle per key.
+    // softmax with the keys distributed over lanes: lane j owns key j (its score, its exponential); max and sum are
+    // warp reductions and p_j is broadcast with one shuffle per key.
 #pragma unroll
     for (int hh = 0; hh < 2; ++hh)
 #pragma unroll
       for (int t = 0; t < NT; ++t) {
         const int nk = slot0 + t + 1;
         float mx = -INFINITY, mine = -INFINITY;
+        if constexpr (NT == 1) {
+          mine = (c.lane < nk) ? rnd<BF>(rnd<BF>(dotk[hh]) * scale) : -INFINITY;
+          mx = mine;
 #pragma unroll
-        for (int j = 0; j < MAXK; ++j) {
-          const float sj = j < nk ? rnd<BF>(rnd<BF>(sc[hh][t][j]) * scale) : -INFINITY;
-          mx = fmaxf(mx, sj);
-          if (j == c.lane) mine = sj;
+          for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        } else {
+#pragma unroll
+          for (int j = 0; j < MAXK; ++j) {
+            const float sj = j < nk ? rnd<BF>(rnd<BF>(sc[hh][t][j]) * scale) : -INFINITY;
+            mx = fmaxf(mx, sj);
+            if (j == c.lane) mine = sj;
+          }
         }
         const float e = (c.lane < nk) ? (BF ? __expf(mine - mx) : expf(mine - mx)) : 0.f;
         float sm = e;

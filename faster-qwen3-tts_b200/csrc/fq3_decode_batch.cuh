@@ -676,14 +676,29 @@ __device__ void attn_small_b(Ctx& c, const StackDev& S, int layer, int slot0_, i
           sc[hh][t][j] = d;
         }
     }
-#pragma unroll
-    for (int o = 16; o; o >>= 1)
+    float dotk[2] = {0.f, 0.f};   // NT == 1: reduce-scatter of the 34 partial dot products (fq3_decode.cuh: rs_step)
+    if constexpr (NT == 1) {
+      float a[34];
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh)
 #pragma unroll
-        for (int t = 0; t < NT; ++t)
+        for (int j = 0; j < 17; ++j) a[hh * 17 + j] = sc[hh][0][j];
+      rs_step<34, 16>(a, c.lane);
+      rs_step<17, 8>(a, c.lane);
+      rs_step<9, 4>(a, c.lane);
+      rs_step<5, 2>(a, c.lane);
+      rs_step<3, 1>(a, c.lane);
+      rs34_gather(a, c.lane, dotk);
+    } else {
 #pragma unroll
-          for (int j = 0; j < MAXK; ++j) sc[hh][t][j] += __shfl_xor_sync(0xffffffffu, sc[hh][t][j], o);
+      for (int o = 16; o; o >>= 1)
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh)
+#pragma unroll
+          for (int t = 0; t < NT; ++t)
+#pragma unroll
+            for (int j = 0; j < MAXK; ++j) sc[hh][t][j] += __shfl_xor_sync(0xffffffffu, sc[hh][t][j], o);
+    }
     Raw vraw[NOLD];
 #pragma unroll
     for (int j = 0; j < NOLD; ++j) {
@@ -696,11 +711,18 @@ __device__ void attn_small_b(Ctx& c, const StackDev& S, int layer, int slot0_, i
       for (int t = 0; t < NT; ++t) {
         const int nk = slot0 + t + 1;
         float mx = -INFINITY, mine = -INFINITY;
+        if constexpr (NT == 1) {
+          mine = (c.lane < nk) ? rnd<BF>(rnd<BF>(dotk[hh]) * scale) : -INFINITY;
+          mx = mine;
 #pragma unroll
-        for (int j = 0; j < MAXK; ++j) {
-          const float sj = j < nk ? rnd<BF>(rnd<BF>(sc[hh][t][j]) * scale) : -INFINITY;
-          mx = fmaxf(mx, sj);
-          if (j == c.lane) mine = sj;
+          for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        } else {
+#pragma unroll
+          for (int j = 0; j < MAXK; ++j) {
+            const float sj = j < nk ? rnd<BF>(rnd<BF>(sc[hh][t][j]) * scale) : -INFINITY;
+            mx = fmaxf(mx, sj);
+            if (j == c.lane) mine = sj;
+          }
         }
         const float e = (c.lane < nk) ? (BF ? __expf(mine - mx) : expf(mine - mx)) : 0.f;
         float sm = e;
